@@ -1,0 +1,464 @@
+#!/usr/bin/env python3
+"""bench.py — queries/sec and GB/s of the VectorBase top-k lookup on B200.
+
+One "step" = one pass of the hot path over one batch of synthetic queries:
+the whole corpus is scored against B queries and the k best rows per query are returned.
+
+Default workload (BASELINE.json `metric`: "top-k cosine on 10M x 768"): configs[2] =
+10M x 768 bf16 corpus, batch 256, top-100, on one B200.  With --gpus N (launched by
+torch.distributed.run, one rank per GPU) the SAME corpus is row-sharded over the N GPUs
+(strong scaling): every rank searches its rows, per-rank candidates are exchanged with one
+NCCL all-gather and merged on every rank.
+
+Output: ONE JSON line (rank 0).  `value` = queries/sec with inputs resident in HBM, timed
+with CUDA events over exactly --steps steps (max over ranks); `e2e` = the same through the
+public host API (pinned host queries -> H2D -> search -> D2H results) inside the timed
+region; `roofline` = the dominant kernel's algorithmic bytes / its event-timed duration
+against MEASURED_PEAKS.json; `cpu_baseline` = the reference algorithm (oracle port, numpy)
+on this box's host cores on a bounded sample.  `--impl reference` times that CPU path alone.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: rows, dim, storage, batch, k, min_score
+    "c1": dict(rows=10_000, dim=384, storage="float32", batch=1, k=10, min_score=0.0,
+               desc="10k x 384 fp32, 1 query, top-10 (tools/benchmark_vectorbase.py)"),
+    "c2": dict(rows=1_000_000, dim=768, storage="bfloat16", batch=64, k=32, min_score=0.0,
+               desc="1M x 768 bf16, batch 64, top-32"),
+    "c3": dict(rows=10_000_000, dim=768, storage="bfloat16", batch=256, k=100, min_score=0.0,
+               desc="10M x 768 bf16, batch 256, top-100"),
+    "c4": dict(rows=10_000_000, dim=1536, storage="float16", batch=1024, k=100, min_score=0.0,
+               desc="10M x 1536 fp16 row-sharded, batch 1024, top-100"),
+    "c5": dict(rows=50_000, dim=384, storage="bfloat16", batch=1000, k=5, min_score=0.0,
+               desc="RelatedTerms 50k x 384, 1000 query terms, top-5"),
+}
+ELEM = {"float32": 4, "bfloat16": 2, "float16": 2}
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    p.add_argument("--workload", choices=sorted(WORKLOADS), default="c3")
+    p.add_argument("--rows", type=int, default=None, help="override corpus rows (experiments)")
+    p.add_argument("--batch", type=int, default=None)
+    p.add_argument("--k", type=int, default=None)
+    p.add_argument("--path", choices=["auto", "scan", "mma"], default="auto")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-sample-rows", type=int, default=400_000)
+    p.add_argument("--cpu-sample-queries", type=int, default=16)
+    return p.parse_args()
+
+
+def algorithmic_bytes(rows, dim, storage, batch, k):
+    """corpus read once per batch + queries + hits."""
+    return rows * dim * ELEM[storage] + batch * dim * 4 + batch * k * 12
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p.get("bf16_tflops"),
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------- CPU side
+def cpu_reference_leg(w, sample_rows, sample_queries, repeats=1):
+    """The reference's algorithm on host cores: one VectorBase lookup per query
+    (np.dot sgemv -> score -> threshold -> argpartition), as every caller of the reference
+    does (storage/memory/reltermsindex.py:326-331), on a bounded sample of the workload:
+    `sample_rows` rows of the corpus (float32, as the reference stores them) x
+    `sample_queries` queries.  Full-corpus q/s is extrapolated linearly in rows (the lookup
+    is a streaming O(N*D) scan)."""
+    from oracle import vectorbase_oracle as O
+
+    rows = min(sample_rows, w["rows"])
+    rng = np.random.default_rng(1234)
+    v = rng.standard_normal((rows, w["dim"]), dtype=np.float32)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    q = rng.standard_normal((sample_queries, w["dim"]), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    O.lookup(v, q[0], w["k"], w["min_score"])  # warm-up (thread pool, page faults)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for qq in q:
+            O.lookup(v, qq, w["k"], w["min_score"])
+        times.append(time.perf_counter() - t0)
+    dt = min(times)
+    all_times = list(times)
+    qps_sample = sample_queries / dt
+    qps_full = qps_sample * rows / w["rows"]
+    threads = os.cpu_count()
+    try:
+        from threadpoolctl import threadpool_info
+
+        blas = [i for i in threadpool_info() if i.get("user_api") == "blas"]
+        if blas:
+            threads = blas[0].get("num_threads", threads)
+    except Exception:
+        pass
+    return {
+        "value": qps_full,
+        "unit": "queries/s",
+        "cores": threads,
+        "kind": "port",
+        "sample": f"{rows} of {w['rows']} rows x {w['dim']} float32, {sample_queries} queries one lookup each "
+                  f"(numpy {np.__version__}), {dt:.3f} s; q/s scaled by rows ratio",
+        "sample_seconds": dt,
+        "all_seconds": all_times,
+        "sample_gbs": rows * w["dim"] * 4 * sample_queries / dt / 1e9,
+    }
+
+
+def run_reference_impl(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # one step = one pass of the sample queries over the sample rows; corpus generated once
+    last = cpu_reference_leg(w, args.cpu_sample_rows, args.cpu_sample_queries,
+                             repeats=args.warmup + args.steps)
+    times = last["all_seconds"][args.warmup:]
+    dt = statistics.fmean(times)
+    rows = min(args.cpu_sample_rows, w["rows"])
+    qps = args.cpu_sample_queries / dt * rows / w["rows"]
+    last["value"] = qps
+    out = {
+        "impl": "reference",
+        "metric": "queries/sec, top-k cosine (VectorBase.fuzzy_lookup_embedding), CPU reference path",
+        "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, w, args.gpus),
+        "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, w, n_gpus):
+    return {
+        "workload": w["desc"], "rows": w["rows"], "dim": w["dim"], "storage": w["storage"],
+        "batch": w["batch"], "k": w["k"], "min_score": w["min_score"],
+        "parallelism": f"row-sharded x{n_gpus}, candidate all-gather" if n_gpus > 1 else "single GPU",
+        "l2": "corpus shard >> 126 MB L2, no flush needed" if w["rows"] * w["dim"] * ELEM[w["storage"]] / n_gpus > 4e8
+              else "corpus fits L2: L2 flushed (256 MB write) between timed steps",
+    }
+
+
+# ----------------------------------------------------------------------------- GPU side
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])), smax.append(float(parts[1])), power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s, p in zip(sm, power) if p > 250] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_shard_on_device(torch, device, lo, hi, dim, storage, seed):
+    """Synthetic unit-norm rows [lo, hi) generated on the GPU in 1M-row blocks (float32
+    standard normal -> row-normalised in float32 -> rounded to the storage dtype), mirroring
+    tools/benchmark_vectorbase.py:80-94.  Block b of the global corpus uses seed + b, so any
+    sharding produces the same corpus."""
+    tdt = {"float32": torch.float32, "bfloat16": torch.bfloat16, "float16": torch.float16}[storage]
+    out = torch.empty((hi - lo, dim), dtype=tdt, device=device)
+    block = 1_000_000
+    gen = torch.Generator(device=device)
+    pos = lo
+    while pos < hi:
+        b = pos // block
+        gen.manual_seed(seed + b)
+        x = torch.randn((block, dim), generator=gen, device=device, dtype=torch.float32)
+        x /= x.norm(dim=1, keepdim=True)
+        start = pos - b * block
+        stop = min(hi - b * block, block)
+        out[pos - lo: pos - lo + (stop - start)] = x[start:stop].to(tdt)
+        pos += stop - start
+        del x
+    return out
+
+
+def run_b200(args, w):
+    import torch
+    import torch.distributed as dist
+
+    import typeagent_py_b200 as tab
+    from typeagent_py_b200.sharded import ShardedVectorBase, shard_bounds
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    rows, dim, storage, batch, k = w["rows"], w["dim"], w["storage"], w["batch"], w["k"]
+    lo, hi = shard_bounds(rows, world)[rank]
+    corpus = make_shard_on_device(torch, device, lo, hi, dim, storage, seed=20260922)
+    torch.cuda.synchronize()
+
+    settings = tab.TextEmbeddingIndexSettings(embedding_model=_NullModel(), min_score=w["min_score"])
+    force = None if args.path == "auto" else args.path
+    if world == 1:
+        base = tab.VectorBase.from_device_tensor(settings, corpus)
+        base.force_path = force
+        sharded = None
+    else:
+        sharded = ShardedVectorBase(settings, device=local_rank, storage_dtype=storage)
+        sharded.load_local_shard(corpus, rows)
+        base = sharded._engine.base
+        base.force_path = force
+
+    rng = np.random.default_rng(7)
+    q_host = torch.empty((batch, dim), dtype=torch.float32).pin_memory()
+    qn = rng.standard_normal((batch, dim)).astype(np.float32)
+    qn /= np.linalg.norm(qn, axis=1, keepdims=True)
+    q_host.copy_(torch.from_numpy(qn))
+    q_dev = q_host.to(device)
+    out_items = torch.empty((batch, k), dtype=torch.int64).pin_memory()
+    out_scores = torch.empty((batch, k), dtype=torch.float32).pin_memory()
+    out_counts = torch.empty((batch,), dtype=torch.int32).pin_memory()
+
+    shard_bytes = (hi - lo) * dim * ELEM[storage]
+    flush = None
+    if shard_bytes < 4e8:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def step_resident():
+        if sharded is None:
+            return base.search_device(q_dev, k, w["min_score"])
+        return sharded.search_tensors(q_dev, k, w["min_score"])
+
+    def step_e2e():
+        # public host API: pinned host queries -> H2D -> search -> D2H of the hits
+        if sharded is None:
+            return base.search_arrays(q_host.numpy(), k, w["min_score"],
+                                      out=(out_items.numpy(), out_scores.numpy(), out_counts.numpy()))
+        qd = q_host.to(device, non_blocking=True)
+        items, scores, counts = sharded.search_tensors(qd, k, w["min_score"])
+        out_items.copy_(items, non_blocking=True)
+        out_scores.copy_(scores, non_blocking=True)
+        out_counts.copy_(counts, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_items, out_scores, out_counts
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, per_step_sync):
+        """Time exactly `steps` steps with CUDA events; returns total ms (this rank)."""
+        total = 0.0
+        if flush is None and not per_step_sync:
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            barrier()
+            return e0.elapsed_time(e1)
+        for _ in range(steps):
+            if flush is not None:
+                flush.fill_(1)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            barrier()
+            total += e0.elapsed_time(e1)
+        return total
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # warm-up (both legs), then the timed regions
+    for _ in range(args.warmup):
+        step_resident()
+        step_e2e()
+    barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_resident = max_over_ranks(timed(step_resident, args.steps, per_step_sync=False))
+    launches_per_step = base.last_timing()["launches"] + (1 if world > 1 else 0)
+    path = base.last_timing()["path"]
+    # e2e: each step ends with a host synchronisation (the D2H result read), so wall == device
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        if flush is not None:
+            flush.fill_(1)
+        step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
+    wall_e2e = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+
+    # roofline pass: the dominant kernel's own duration (events inside libtavec), per step
+    scan_ms = []
+    for _ in range(args.steps):
+        if flush is not None:
+            flush.fill_(1)
+        step_resident()
+        scan_ms.append(base.last_timing()["scan_ms"])
+    kernel_ms = statistics.fmean(scan_ms)
+
+    # sanity: the result of the last step is well-formed
+    items, scores, counts = step_resident()
+    torch.cuda.synchronize()
+    assert int(counts.min()) == min(k, rows) and bool((scores[:, :-1] >= scores[:, 1:]).all())
+    assert int(items.min()) >= 0 and int(items.max()) < rows
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    ms_step = ms_resident / args.steps
+    qps = batch / (ms_step / 1e3)
+    e2e_ms_step = ms_e2e / args.steps
+    # per-GPU dominant kernel: this rank's shard is read once per pass of the kernel
+    passes = 1 if path == "mma" else -(-batch // 8)
+    algo_bytes = algorithmic_bytes(hi - lo, dim, storage, batch, k)
+    algo_launch_bytes = (hi - lo) * dim * ELEM[storage] * passes + batch * dim * 4 + batch * k * 12
+    achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
+    out = {
+        "metric": "queries/sec, top-k cosine (VectorBase.fuzzy_lookup_embedding) on "
+                  f"{rows}x{dim} {storage}, batch {batch}, top-{k}",
+        "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": {"float32": "f32", "bfloat16": "bf16", "float16": "f16"}[storage] + " in, f32 accumulate",
+        "data": "synthetic (unit-norm gaussian rows, generated on device; seeds in bench.py)",
+        "config": {**workload_config(args, w, world), "path": path},
+        "gb_per_s": algorithmic_bytes(rows, dim, storage, batch, k) / (ms_step / 1e3) / 1e9,
+        "e2e": {"value": batch / (e2e_ms_step / 1e3), "unit": "queries/s",
+                "h2d_bytes_per_step": batch * dim * 4, "d2h_bytes_per_step": batch * k * 12 + batch * 4,
+                "ms_per_step": e2e_ms_step, "wall_ms_per_step": wall_e2e * 1e3 / args.steps,
+                "api": "VectorBase.search_arrays(host float32 queries) -> host int64/float32 hits"},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": {
+            "bound": "hbm", "kernel": "scan_rows_kernel" if path == "scan" else "mma_topk_kernel",
+            "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "of": peaks["source"], "traffic": None, "kernel_ms_per_step": kernel_ms,
+            "algorithmic_bytes_per_step": algo_bytes,
+            "bytes_actually_requested_per_step": algo_launch_bytes,
+            "note": "achieved = algorithmic bytes (corpus shard read once per batch) / event-timed duration of "
+                    "the dominant kernel(s) per step" + ("" if passes == 1 else
+                    f"; the row-scan path re-reads the corpus once per 8 queries ({passes} passes)"),
+        },
+        "clocks": clocks,
+    }
+    if peaks.get("bf16_tflops"):
+        flops = 2.0 * batch * (hi - lo) * dim
+        out["roofline"]["tensor_tflops"] = flops / (kernel_ms / 1e3) / 1e12
+        out["roofline"]["tensor_frac_of_burst"] = out["roofline"]["tensor_tflops"] / peaks["bf16_tflops"]
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference_leg(w, args.cpu_sample_rows, args.cpu_sample_queries)
+        out["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+        out["cpu_baseline"]["sample_gbs"] = cb["sample_gbs"]
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class _NullModel:
+    model_name = "bench-null"
+
+    def add_embedding(self, key, embedding):
+        return None
+
+
+def main():
+    args = parse_args()
+    w = dict(WORKLOADS[args.workload])
+    for name in ("rows", "batch", "k"):
+        if getattr(args, name) is not None:
+            w[name] = getattr(args, name)
+            w["desc"] += f" [{name}={w[name]}]"
+    if args.impl == "reference":
+        run_reference_impl(args, w)
+    else:
+        run_b200(args, w)
+
+
+if __name__ == "__main__":
+    main()

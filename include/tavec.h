@@ -1,0 +1,144 @@
+/*
+ * tavec.h — C ABI of libtavec.so, the B200 (sm_100a) engine behind typeagent's
+ * VectorBase top-k lookup.
+ *
+ * This is the drop-in boundary for ONE path of microsoft/typeagent-py:
+ *
+ *   src/typeagent/aitools/vectorbase.py:163-201  VectorBase.fuzzy_lookup_embedding
+ *   src/typeagent/aitools/vectorbase.py:203-230  VectorBase.fuzzy_lookup_embedding_in_subset
+ *   src/typeagent/aitools/vectorbase.py:115-148  add_embedding / add_embeddings  (append)
+ *   src/typeagent/aitools/vectorbase.py:253-287  clear / serialize / deserialize (bulk load)
+ *   src/typeagent/aitools/vectorbase.py:44-47    cosine_to_score
+ *
+ * The reference has no FFI of its own (it is pure Python + numpy); these entry points
+ * are what a ctypes binding for that path binds.  Plain pointers
+ * and sizes only; no torch / numpy types.  Every function returns 0 on success or a
+ * negative tav_status; tav_last_error() returns a thread-local message for the last
+ * failure.  There is no CPU fallback anywhere behind this ABI: without a CUDA device
+ * every compute entry point fails with TAV_ERR_CUDA.
+ *
+ * Threading: an index may be used from one thread at a time.  Work is enqueued on the
+ * caller's stream (`stream`, a cudaStream_t passed as void*; NULL = the index's own
+ * stream).  Entry points that take host output pointers synchronise that stream before
+ * returning; with TAV_OUTPUTS_ON_DEVICE they return as soon as the work is enqueued.
+ */
+#ifndef TAVEC_H
+#define TAVEC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAV_ABI_VERSION 1
+
+typedef struct tav_index tav_index; /* opaque: device corpus + workspace + stream */
+
+/* storage / source element types */
+enum tav_dtype { TAV_F32 = 0, TAV_BF16 = 1, TAV_F16 = 2 };
+
+enum tav_status {
+    TAV_OK = 0,
+    TAV_ERR_INVALID = -1, /* bad argument (the Python side maps this to ValueError) */
+    TAV_ERR_CUDA = -2,    /* CUDA runtime / driver failure, or no device  (RuntimeError) */
+    TAV_ERR_OOM = -3,     /* device or pinned-host allocation failed      (MemoryError) */
+    TAV_ERR_RANGE = -4,   /* ordinal out of range                         (IndexError) */
+    TAV_ERR_STATE = -5    /* operation not valid in this state (e.g. append to adopted memory) */
+};
+
+/* tav_create flags */
+enum tav_index_flags {
+    /* L2-normalise every appended row (fused into the convert-on-append kernel) and every
+     * query (fused into query staging): cosine similarity for un-normalised inputs.  The
+     * default (0) is the reference's behaviour: a plain dot product that relies on the
+     * caller's unit-norm embeddings (vectorbase.py:176, model_adapters.py:176-184). */
+    TAV_NORMALIZE = 1
+};
+
+/* tav_search flags */
+enum tav_search_flags {
+    TAV_QUERIES_ON_DEVICE = 1, /* `queries` is a device pointer (float32 [n_queries, dim]) */
+    TAV_OUTPUTS_ON_DEVICE = 2, /* out_* are device pointers; no synchronisation */
+    TAV_FORCE_SCAN = 4,        /* use the CUDA-core row-scan kernels whatever the shape */
+    TAV_FORCE_MMA = 8          /* use the tcgen05 tensor-core kernel (bf16/fp16 storage only) */
+};
+
+int tav_abi_version(void);
+const char* tav_last_error(void);
+int tav_device_count(int* out_count);
+
+/* Lifecycle.  `dim` may be 0: adopted from the first append (vectorbase.py:119-121).
+ * `reserve_rows` pre-sizes the device buffer (growth is by capacity doubling). */
+int tav_create(int device, int dim, int store_dtype, int index_flags, int64_t reserve_rows,
+               tav_index** out);
+int tav_destroy(tav_index* ix);
+int tav_clear(tav_index* ix); /* size -> 0; dim and capacity kept (vectorbase.py:253-256) */
+int tav_reserve(tav_index* ix, int64_t rows);
+
+/* Append `n` rows of `dim` elements of `src_dtype` from host (src_on_device = 0) or device
+ * memory; converted to the storage dtype with round-to-nearest-even on the GPU. */
+int tav_append(tav_index* ix, const void* rows, int64_t n, int dim, int src_dtype,
+               int src_on_device, void* stream);
+
+/* Zero-copy: use caller-owned device memory (`n` rows of storage dtype, row-major, dense,
+ * 16-byte aligned) as the corpus.  The caller keeps it alive; append is then invalid. */
+int tav_adopt_device(tav_index* ix, void* device_rows, int64_t n, int dim);
+
+int64_t tav_size(const tav_index* ix);
+int tav_dim(const tav_index* ix);
+int tav_store_dtype(const tav_index* ix);
+int tav_device(const tav_index* ix);
+
+/* Read rows [first, first+n) back as float32 into host memory (storage -> f32 is exact). */
+int tav_read_rows(tav_index* ix, int64_t first, int64_t n, float* out_host, void* stream);
+
+/*
+ * The hot path.  For each of `n_queries` query vectors (float32 [n_queries, dim]):
+ *   x      = dot(row, query)                       float32 accumulate
+ *   score  = clip((x + 1) / 2, 0, 1)               float32, as vectorbase.py:44-47
+ *   keep rows with score >= min_score              float32 compare, as :179
+ *   return the `k` best, descending by score (equal scores: higher row first)
+ * Rows are the whole corpus, or — if `subset` != NULL — the `subset_len` host int64
+ * ordinals in `subset` (negative ordinals count from the end like numpy; duplicates are
+ * scored and returned once per occurrence; vectorbase.py:217-218).
+ *
+ *   out_items  [n_queries, k] int64   row ordinal + item_offset (or the subset ordinal)
+ *   out_scores [n_queries, k] float32
+ *   out_counts [n_queries]    int32   number of valid entries per query (<= k)
+ *
+ * k must be >= 1 (the caller turns the reference's "max_hits == 0 means everything",
+ * quirk Q2, into k = number of rows).  Any k is accepted; above TAV_PASS_K rows per
+ * query the search runs in several passes.
+ */
+int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float min_score,
+               int flags, const int64_t* subset, int64_t subset_len, int64_t item_offset,
+               int64_t* out_items, float* out_scores, int32_t* out_counts, void* stream);
+
+/*
+ * Merge step of the row-sharded search: `n_lists` per-shard results of
+ * tav_search (device memory, as an all-gather of each rank's outputs produces) -> the
+ * global top-k per query, same order rule.  List g's arrays start at
+ *   items + g * items_stride   ([n_queries, k] int64;  stride in int64 elements)
+ *   scores + g * scores_stride ([n_queries, k] float32; stride in float elements)
+ *   counts + g * counts_stride ([n_queries] int32;      stride in int32 elements)
+ * (a stride of 0 means dense: n_queries*k, n_queries*k, n_queries), which lets one packed
+ * all-gather buffer per rank be merged in place.  Lists must be in ascending shard (row)
+ * order.  All pointers are device pointers on `device`; outputs are [n_queries, k] /
+ * [n_queries].
+ */
+int tav_merge_topk(int device, int n_lists, int n_queries, int k, const int64_t* items,
+                   const float* scores, const int32_t* counts, int64_t items_stride,
+                   int64_t scores_stride, int64_t counts_stride, int64_t* out_items,
+                   float* out_scores, int32_t* out_counts, void* stream);
+
+/* Device time of the last tav_search on this index, measured with CUDA events on the
+ * search's stream: `scan_ms` = the dominant kernel(s) (row scan or MMA kernel, summed over
+ * query chunks), `total_ms` = first launch to last result byte on device; `launches` =
+ * kernels launched; `path` = 1 row-scan kernels, 2 tcgen05 kernel.  Synchronises. */
+int tav_last_timing(tav_index* ix, float* scan_ms, float* total_ms, int* launches, int* path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAVEC_H */

@@ -1,0 +1,106 @@
+"""ctypes binding of libtavec.so (``include/tavec.h``) — the only way Python reaches the GPU.
+
+Fails loudly: a missing library, a missing symbol or a missing CUDA device raise
+``RuntimeError``; nothing here or above it computes on the CPU instead.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtavec.so")
+
+TAV_F32, TAV_BF16, TAV_F16 = 0, 1, 2
+DTYPE_CODES = {"float32": TAV_F32, "bfloat16": TAV_BF16, "float16": TAV_F16}
+DTYPE_NAMES = {v: k for k, v in DTYPE_CODES.items()}
+
+TAV_NORMALIZE = 1
+TAV_QUERIES_ON_DEVICE, TAV_OUTPUTS_ON_DEVICE, TAV_FORCE_SCAN, TAV_FORCE_MMA = 1, 2, 4, 8
+
+TAV_ERR_INVALID, TAV_ERR_CUDA, TAV_ERR_OOM, TAV_ERR_RANGE, TAV_ERR_STATE = -1, -2, -3, -4, -5
+
+# every symbol include/tavec.h declares: (name, restype, argtypes)
+_i64p = C.POINTER(C.c_int64)
+_f32p = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int32)
+SIGNATURES = {
+    "tav_abi_version": (C.c_int, []),
+    "tav_last_error": (C.c_char_p, []),
+    "tav_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "tav_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    "tav_destroy": (C.c_int, [C.c_void_p]),
+    "tav_clear": (C.c_int, [C.c_void_p]),
+    "tav_reserve": (C.c_int, [C.c_void_p, C.c_int64]),
+    "tav_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tav_adopt_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    "tav_size": (C.c_int64, [C.c_void_p]),
+    "tav_dim": (C.c_int, [C.c_void_p]),
+    "tav_store_dtype": (C.c_int, [C.c_void_p]),
+    "tav_device": (C.c_int, [C.c_void_p]),
+    "tav_read_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "tav_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int,
+                             C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.c_void_p]),
+    "tav_merge_topk": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int64, C.c_int64, C.c_int64,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tav_last_timing": (C.c_int, [C.c_void_p, _f32p, _f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """Load libtavec.so once and bind every declared symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python typeagent-py_b200/build.py` "
+                "(or __graft_entry__.build()).  There is no CPU fallback."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:  # pragma: no cover - build mismatch
+                raise RuntimeError(f"libtavec.so does not export {name}") from e
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.tav_abi_version() != 1:
+            raise RuntimeError(f"libtavec.so ABI version {lib.tav_abi_version()} != 1; rebuild")
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    msg = load().tav_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int) -> None:
+    """Map a negative tav_status to the exception the reference would raise."""
+    if rc >= 0:
+        return
+    msg = last_error() or f"libtavec error {rc}"
+    if rc == TAV_ERR_INVALID:
+        raise ValueError(msg)
+    if rc == TAV_ERR_RANGE:
+        raise IndexError(msg)
+    if rc == TAV_ERR_OOM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(load().tav_device_count(C.byref(n)))
+    return n.value

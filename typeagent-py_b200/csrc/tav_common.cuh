@@ -1,0 +1,109 @@
+// tav_common.cuh — shared device/host helpers of libtavec (sm_100a).
+//
+// Candidate keys.  Every (row, score) candidate travels as one 64-bit key
+//     key = (float_bits(score) << 32) | position
+// where score = clip((x + 1) / 2, 0, 1) in float32 (reference: aitools/vectorbase.py:44-47)
+// is non-negative, so its IEEE bit pattern is monotone in its value, and `position` is the
+// row ordinal (or the position inside the caller's subset).  Sorting keys descending gives
+// the library's total order: higher score first, equal scores -> higher position first
+// (what numpy's reversed argsort yields for small tied groups, vectorbase.py:184-187).
+// Keys are unique per scanned row, which makes the multi-pass "next page" search exact.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tav {
+
+constexpr int kPassK = 2048;        // most hits one pass returns per query (TAV_PASS_K)
+constexpr int kScanThreads = 256;   // row-scan CTA: 8 warps
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kSelectThreads = 256;
+
+// score map, exactly the reference's float32 arithmetic: (x + 1.0f) / 2.0f == (x + 1.0f) * 0.5f
+// bit for bit (scaling by a power of two is exact), with the add kept un-fused.
+__device__ __forceinline__ float score_from_dot(float x) {
+    float s = __fmul_rn(__fadd_rn(x, 1.0f), 0.5f);
+    s = s < 0.0f ? 0.0f : s;   // NaN falls through both clamps and is rejected by `s >= floor`
+    s = s > 1.0f ? 1.0f : s;
+    return s;
+}
+
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t pos) {
+    return (static_cast<uint64_t>(__float_as_uint(score)) << 32) | pos;
+}
+__device__ __forceinline__ float key_score(uint64_t key) {
+    return __uint_as_float(static_cast<uint32_t>(key >> 32));
+}
+__device__ __forceinline__ uint32_t key_pos(uint64_t key) { return static_cast<uint32_t>(key); }
+
+// In-place bitonic sort, descending, of n (power of two) keys in shared memory by the whole
+// CTA.  Callers pad unused slots with 0 (the smallest key; a real key 0 ties harmlessly).
+template <int THREADS>
+__device__ __forceinline__ void bitonic_sort_desc(uint64_t* a, int n) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (n >> 1); t += THREADS) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const uint64_t x = a[lo], y = a[hi];
+                if ((x < y) == desc) {
+                    a[lo] = y;
+                    a[hi] = x;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Shared-memory candidate list of one query, owned by a CTA.  Protocol: pushes happen only
+// between two CTA-wide barriers ("a round") and a round pushes at most `round_max` keys.
+// list_push() reports whether the list has risen above its watermark (cap - round_max); the
+// CTA ORs those reports at the round barrier (__syncthreads_or — exact, because the final
+// count is the largest slot any pusher was given) and, when set, every thread takes the slow
+// path together and compacts the lists that need it (sort, keep best k, raise the admission
+// threshold to just above the k-th key).  One barrier per round in the common case.
+struct CandList {
+    uint64_t* keys;  // [cap]
+    int* count;      // number of keys pushed so far this epoch
+    uint64_t* admit; // keys >= *admit are admitted
+};
+
+template <int THREADS>
+__device__ __forceinline__ void list_compact(CandList l, int cap, int k, uint64_t floor_key) {
+    // all threads call; *l.count is stable (callers barrier first)
+    const int n = min(*l.count, cap);
+    for (int i = n + threadIdx.x; i < cap; i += THREADS) l.keys[i] = 0;
+    bitonic_sort_desc<THREADS>(l.keys, cap);
+    if (threadIdx.x == 0) {
+        const int kept = min(n, k);
+        *l.count = kept;
+        *l.admit = (kept == k) ? l.keys[k - 1] + 1 : floor_key;
+    }
+    __syncthreads();
+}
+
+// returns 1 when the list is now above `watermark` (compaction needed before the next round)
+__device__ __forceinline__ int list_push(CandList l, uint64_t key, int watermark) {
+    const int slot = atomicAdd(l.count, 1);
+    l.keys[slot] = key;  // room guaranteed by the round protocol
+    return slot + 1 > watermark;
+}
+
+inline int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// element loaders: storage type -> float
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
+
+}  // namespace tav

@@ -1,0 +1,87 @@
+// tav_internal.h — launch interfaces between the translation units of libtavec.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tavec.h"
+
+namespace tav {
+
+// ---- row-scan path (tav_scan.cu) -------------------------------------------------------
+struct ScanArgs {
+    const void* corpus;       // [n_corpus, dim] storage dtype, row-major dense
+    int dtype;                // tav_dtype
+    int64_t n_corpus;
+    int dim;
+    const int64_t* subset;    // device, or nullptr = all rows
+    int64_t n_scan;           // rows scanned (subset_len or n_corpus)
+    const float* queries;     // device float32 [nq, dim]
+    int nq;                   // 1..8 queries scored per pass over the rows
+    float floor_score;        // (float)min_score
+    const uint64_t* bound;    // per query: admit only keys < bound (multi-pass), or nullptr
+    int k;                    // hits kept per query this pass (<= kPassK)
+    uint64_t* cand_keys;      // [nq, cand_stride] per-query global candidate buffers
+    int cand_stride;
+    uint32_t* cand_count;     // [nq], zeroed by the caller
+    int grid;                 // CTAs to launch (cand_stride >= grid * k)
+};
+int scan_max_queries(int dim, int k);            // how many queries one pass can take (smem)
+int scan_grid(int device, int dtype, int dim, int nq, int k, int64_t n_scan);
+cudaError_t launch_scan(const ScanArgs& a, cudaStream_t s);
+
+struct SelectArgs {
+    const uint64_t* cand_keys;   // [nq, cand_stride]
+    int cand_stride;
+    const uint32_t* cand_count;  // [nq]
+    int nq;
+    int k;                       // hits this pass
+    int out_stride;              // row stride of out_items/out_scores (the caller's total k)
+    int out_offset;              // column where this pass starts
+    const int64_t* subset;       // device copy of the caller's ordinals, or nullptr
+    int64_t item_offset;
+    int64_t* out_items;          // already offset to the first query of this chunk
+    float* out_scores;
+    int32_t* out_counts;
+    uint64_t* bound_out;         // [nq] next-pass bound (last key, 0 if exhausted), or nullptr
+    int accumulate;              // counts += n instead of counts = n
+};
+cudaError_t launch_select(const SelectArgs& a, cudaStream_t s);
+
+cudaError_t launch_merge(int n_lists, int n_queries, int k, const int64_t* items,
+                         const float* scores, const int32_t* counts, int64_t items_stride,
+                         int64_t scores_stride, int64_t counts_stride, int64_t* out_items,
+                         float* out_scores, int32_t* out_counts, cudaStream_t s);
+
+// rows [n, dim] of src dtype -> dst dtype (RNE), optionally L2-normalised per row (fp32 math)
+cudaError_t launch_convert(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
+                           int dim, int normalize, cudaStream_t s);
+
+// ---- tensor-core path (tav_mma.cu) -----------------------------------------------------
+struct MmaPlan;  // opaque: tensor maps + workspace for one (index, batch shape)
+bool mma_supported(int dtype, int dim);
+// returns cudaSuccess and fills outputs exactly like scan+select; see tav_mma.cu
+struct MmaArgs {
+    int device;
+    const void* corpus;
+    int dtype;
+    int64_t n_corpus;
+    int dim;
+    const float* queries;  // device float32 [nq, dim]
+    int nq;
+    float floor_score;
+    int k;
+    int64_t item_offset;
+    int64_t* out_items;    // device [nq, k]
+    float* out_scores;
+    int32_t* out_counts;
+    int32_t* retry_flags;  // device [nq]: set to 1 for queries the caller must redo with the row scan
+    cudaEvent_t ev_main_begin, ev_main_end;  // recorded around the dominant kernel (may be null)
+};
+size_t mma_workspace_bytes(const MmaArgs& a);
+cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspace_bytes,
+                              cudaStream_t s, int* launches);
+
+void set_error(const char* fmt, ...);
+
+}  // namespace tav

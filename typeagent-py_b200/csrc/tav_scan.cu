@@ -1,0 +1,488 @@
+// tav_scan.cu — the CUDA-core "row scan" path of libtavec: exact float32 dot products for a
+// handful of queries at a time, HBM-bound (reads every corpus row once per pass).
+//
+// Replaces, on the GPU, the body of the reference's VectorBase.fuzzy_lookup_embedding /
+// fuzzy_lookup_embedding_in_subset (aitools/vectorbase.py:163-230):
+//     np.dot(V, e) -> cosine_to_score -> flatnonzero(>= min_score) -> argpartition/argsort
+// as ONE fused kernel (dot + score map + threshold + running top-k in shared memory) plus a
+// one-CTA-per-query select kernel that merges the per-CTA survivors.  No score vector, mask
+// or gather copy is ever materialised.
+//
+// Layout: corpus row-major [N, D] in HBM (float32 / bf16 / fp16), queries float32 [nq, D]
+// staged in shared memory, one warp per row, 4 rows in flight per warp, 16-byte vector loads
+// (float4 / 8 x 16-bit) with a scalar fallback for rows that are not 16-byte multiples.
+// Algorithmic bytes per pass: n_scan * D * sizeof(storage) (+ nq*D*4 queries, + hits).
+
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "tav_common.cuh"
+#include "tav_internal.h"
+
+namespace tav {
+
+constexpr int kRowsPerWarp = 4;
+constexpr int kRoundRows = kScanWarps * kRowsPerWarp;  // 32 rows per CTA round
+constexpr int kScanSmemBudget = 160 * 1024;
+
+static inline int scan_cap(int k) {
+    int c = next_pow2(2 * k);
+    if (c < 128) c = 128;  // >= k + kRoundRows always
+    return c;
+}
+static inline size_t scan_smem_bytes(int qb, int dim, int k) {
+    size_t q_bytes = (static_cast<size_t>(qb) * dim * sizeof(float) + 15) & ~size_t(15);
+    return q_bytes + static_cast<size_t>(qb) * scan_cap(k) * sizeof(uint64_t);
+}
+
+int scan_max_queries(int dim, int k) {
+    for (int qb = 8; qb >= 1; qb >>= 1)
+        if (scan_smem_bytes(qb, dim, k) <= static_cast<size_t>(kScanSmemBudget)) return qb;
+    return 0;
+}
+
+// ---- 16-byte row chunk -> floats ---------------------------------------------------------
+template <typename T>
+struct Vec;
+template <>
+struct Vec<float> {
+    static constexpr int kElems = 4;
+    __device__ static __forceinline__ void load(const float* p, float (&f)[4]) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
+        f[0] = v.x, f[1] = v.y, f[2] = v.z, f[3] = v.w;
+    }
+};
+template <>
+struct Vec<__nv_bfloat16> {
+    static constexpr int kElems = 8;
+    __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            f[2 * i] = __uint_as_float(w[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+        }
+    }
+};
+template <>
+struct Vec<__half> {
+    static constexpr int kElems = 8;
+    __device__ static __forceinline__ void load(const __half* p, float (&f)[8]) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            f[2 * i] = t.x, f[2 * i + 1] = t.y;
+        }
+    }
+};
+
+// Butterfly that leaves, in every lane, the warp-wide sum of value (lane >> (5 - log2 NV)):
+// 31 shuffles for 32 values instead of 160.
+template <int NV>
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[NV], int lane) {
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    int n = NV;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (n > 1) {
+            n >>= 1;
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < NV / 2; ++i) {
+                if (i < n) {
+                    const float send = upper ? v[i] : v[i + n];
+                    const float keep = upper ? v[i + n] : v[i];
+                    v[i] = keep + __shfl_xor_sync(kFull, send, off);
+                }
+            }
+        } else {
+            v[0] += __shfl_xor_sync(kFull, v[0], off);
+        }
+    }
+}
+
+template <typename T, int QB, bool VEC>
+__global__ void __launch_bounds__(kScanThreads) scan_rows_kernel(const ScanArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NV = kRowsPerWarp * QB;
+    const int dim = a.dim;
+    const int cap = max(128, 1 << (32 - __clz(2 * a.k - 1)));  // == scan_cap(k)
+    float* sq = reinterpret_cast<float*>(smem_raw);
+    const size_t q_bytes = (static_cast<size_t>(QB) * dim * sizeof(float) + 15) & ~size_t(15);
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw + q_bytes);
+    __shared__ int s_cnt[QB];
+    __shared__ uint64_t s_admit[QB];
+    __shared__ uint32_t s_base[QB];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t floor_key = 0;  // the floor itself is tested in float (NaN-safe)
+
+    // stage the queries (zero-fill unused slots)
+    for (int i = tid; i < QB * dim; i += kScanThreads) {
+        const int q = i / dim;
+        sq[i] = q < a.nq ? a.queries[i] : 0.0f;
+    }
+    if (tid < QB) {
+        s_cnt[tid] = 0;
+        s_admit[tid] = floor_key;
+    }
+
+    const T* corpus = reinterpret_cast<const T*>(a.corpus);
+    const int64_t n_tiles = (a.n_scan + kRoundRows - 1) / kRoundRows;
+
+    int need = 0;  // my last push left a list above its watermark
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // round barrier: previous pushes visible (first round: queries staged)
+        if (__syncthreads_or(need)) {
+            need = 0;
+#pragma unroll
+            for (int q = 0; q < QB; ++q) {
+                if (s_cnt[q] > cap - kRoundRows) {  // CTA-uniform: nobody pushes in here
+                    CandList l{skeys + static_cast<size_t>(q) * cap, &s_cnt[q], &s_admit[q]};
+                    list_compact<kScanThreads>(l, cap, a.k, floor_key);
+                }
+            }
+        }
+
+        const int64_t pos0 = tile * kRoundRows + warp * kRowsPerWarp;
+        const T* rp[kRowsPerWarp];
+#pragma unroll
+        for (int r = 0; r < kRowsPerWarp; ++r) {
+            const int64_t pos = pos0 + r;
+            int64_t row = 0;
+            if (pos < a.n_scan) {
+                row = pos;
+                if (a.subset) {
+                    row = a.subset[pos];
+                    if (row < 0) row += a.n_corpus;  // numpy-style negative ordinals
+                }
+            }
+            rp[r] = corpus + row * dim;
+        }
+
+        float acc[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
+
+        if constexpr (VEC) {
+            constexpr int E = Vec<T>::kElems;
+            const int nvec = dim / E;
+            for (int c = lane; c < nvec; c += 32) {
+                float f[kRowsPerWarp][E];
+#pragma unroll
+                for (int r = 0; r < kRowsPerWarp; ++r) Vec<T>::load(rp[r] + c * E, f[r]);
+#pragma unroll
+                for (int q = 0; q < QB; ++q) {
+                    const float4* q4 = reinterpret_cast<const float4*>(sq + q * dim + c * E);
+#pragma unroll
+                    for (int h = 0; h < E / 4; ++h) {
+                        const float4 qv = q4[h];
+#pragma unroll
+                        for (int r = 0; r < kRowsPerWarp; ++r) {
+                            float s = acc[r * QB + q];
+                            s = fmaf(f[r][4 * h + 0], qv.x, s);
+                            s = fmaf(f[r][4 * h + 1], qv.y, s);
+                            s = fmaf(f[r][4 * h + 2], qv.z, s);
+                            s = fmaf(f[r][4 * h + 3], qv.w, s);
+                            acc[r * QB + q] = s;
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int c = lane; c < dim; c += 32) {
+                float f[kRowsPerWarp];
+#pragma unroll
+                for (int r = 0; r < kRowsPerWarp; ++r) f[r] = to_float(rp[r][c]);
+#pragma unroll
+                for (int q = 0; q < QB; ++q) {
+                    const float qv = sq[q * dim + c];
+#pragma unroll
+                    for (int r = 0; r < kRowsPerWarp; ++r)
+                        acc[r * QB + q] = fmaf(f[r], qv, acc[r * QB + q]);
+                }
+            }
+        }
+
+        warp_transpose_reduce<NV>(acc, lane);
+
+        constexpr int kLanesPerValue = 32 / NV;
+        if ((lane & (kLanesPerValue - 1)) == 0) {
+            const int idx = lane / kLanesPerValue;
+            const int r = idx / QB, q = idx % QB;
+            const int64_t pos = pos0 + r;
+            if (pos < a.n_scan && q < a.nq) {
+                const float s = score_from_dot(acc[0]);
+                if (s >= a.floor_score) {  // float32 compare, as vectorbase.py:179
+                    const uint64_t key = make_key(s, static_cast<uint32_t>(pos));
+                    if (key >= s_admit[q] && (a.bound == nullptr || key < a.bound[q])) {
+                        CandList l{skeys + static_cast<size_t>(q) * cap, &s_cnt[q], &s_admit[q]};
+                        need |= list_push(l, key, cap - kRoundRows);
+                    }
+                }
+            }
+        }
+    }
+
+    // hand the CTA's best k per query to the global candidate buffers
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+        if (q >= a.nq) break;
+        CandList l{skeys + static_cast<size_t>(q) * cap, &s_cnt[q], &s_admit[q]};
+        if (s_cnt[q] > a.k) list_compact<kScanThreads>(l, cap, a.k, floor_key);
+        const int n = s_cnt[q];
+        if (tid == 0 && n > 0) s_base[q] = atomicAdd(&a.cand_count[q], static_cast<uint32_t>(n));
+        __syncthreads();
+        if (n > 0) {
+            uint64_t* dst = a.cand_keys + static_cast<size_t>(q) * a.cand_stride + s_base[q];
+            for (int i = tid; i < n; i += kScanThreads) dst[i] = l.keys[i];
+        }
+    }
+}
+
+int scan_grid(int device, int dtype, int dim, int nq, int k, int64_t n_scan) {
+    (void)dtype;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const size_t smem = scan_smem_bytes(nq, dim, k);
+    int per_sm = static_cast<int>((200 * 1024) / (smem + 1024));
+    if (per_sm > 4) per_sm = 4;   // 32 warps x 4 rows in flight already covers HBM latency
+    if (per_sm < 1) per_sm = 1;
+    int64_t tiles = (n_scan + kRoundRows - 1) / kRoundRows;
+    int64_t g = static_cast<int64_t>(sms) * per_sm;
+    if (g > tiles) g = tiles;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+template <typename T, int QB>
+static cudaError_t launch_scan_t(const ScanArgs& a, cudaStream_t s) {
+    const size_t row_bytes = static_cast<size_t>(a.dim) * sizeof(T);
+    const bool vec = (row_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(a.corpus) % 16 == 0);
+    const size_t smem = scan_smem_bytes(QB, a.dim, a.k);
+    auto kern = vec ? scan_rows_kernel<T, QB, true> : scan_rows_kernel<T, QB, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    kern<<<a.grid, kScanThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_scan_q(const ScanArgs& a, cudaStream_t s) {
+    if (a.nq <= 1) return launch_scan_t<T, 1>(a, s);
+    if (a.nq <= 2) return launch_scan_t<T, 2>(a, s);
+    if (a.nq <= 4) return launch_scan_t<T, 4>(a, s);
+    return launch_scan_t<T, 8>(a, s);
+}
+
+cudaError_t launch_scan(const ScanArgs& a, cudaStream_t s) {
+    switch (a.dtype) {
+        case TAV_F32: return launch_scan_q<float>(a, s);
+        case TAV_BF16: return launch_scan_q<__nv_bfloat16>(a, s);
+        case TAV_F16: return launch_scan_q<__half>(a, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ---- select: per query, best k of the global candidate buffer, sorted, decoded -----------
+static inline int select_cap(int k) { return next_pow2(k + kSelectThreads); }
+
+__global__ void __launch_bounds__(kSelectThreads) select_kernel(const SelectArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+    __shared__ int s_cnt;
+    __shared__ uint64_t s_admit;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int cap = 1 << (32 - __clz(a.k + kSelectThreads - 1));
+    const uint32_t total = min(a.cand_count[q], static_cast<uint32_t>(a.cand_stride));
+    const uint64_t* in = a.cand_keys + static_cast<size_t>(q) * a.cand_stride;
+    if (tid == 0) {
+        s_cnt = 0;
+        s_admit = 0;
+    }
+    CandList l{keys, &s_cnt, &s_admit};
+    int need = 0;
+    for (uint32_t base = 0; base < total; base += kSelectThreads) {
+        if (__syncthreads_or(need)) {
+            need = 0;
+            list_compact<kSelectThreads>(l, cap, a.k, 0);
+        }
+        const uint32_t i = base + tid;
+        if (i < total) {
+            const uint64_t key = in[i];
+            if (key >= s_admit) need |= list_push(l, key, cap - kSelectThreads);
+        }
+    }
+    __syncthreads();
+    list_compact<kSelectThreads>(l, cap, a.k, 0);  // final sort (also when total == 0)
+    const int n = s_cnt;
+    int64_t* items = a.out_items + static_cast<size_t>(q) * a.out_stride + a.out_offset;
+    float* scores = a.out_scores + static_cast<size_t>(q) * a.out_stride + a.out_offset;
+    for (int j = tid; j < a.k; j += kSelectThreads) {
+        if (j < n) {
+            const uint64_t key = keys[j];
+            const uint32_t pos = key_pos(key);
+            const int64_t item = a.subset ? a.subset[pos] : static_cast<int64_t>(pos);
+            items[j] = item + a.item_offset;
+            scores[j] = key_score(key);
+        } else {
+            items[j] = -1;
+            scores[j] = 0.0f;
+        }
+    }
+    if (tid == 0) {
+        a.out_counts[q] = a.accumulate ? a.out_counts[q] + n : n;
+        if (a.bound_out) a.bound_out[q] = (n == a.k) ? keys[a.k - 1] : 0;
+    }
+}
+
+cudaError_t launch_select(const SelectArgs& a, cudaStream_t s) {
+    const size_t smem = static_cast<size_t>(select_cap(a.k)) * sizeof(uint64_t);
+    cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    select_kernel<<<a.nq, kSelectThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+// ---- merge of per-shard results (after the candidate all-gather) -------------------------
+// key low word = list * k + (k - 1 - j): among equal scores a later shard (higher rows) and,
+// inside a shard, an earlier slot (higher row) sorts first — the same total order as one GPU.
+__global__ void __launch_bounds__(kSelectThreads)
+merge_kernel(int n_lists, int n_queries, int k, const int64_t* items, const float* scores,
+             const int32_t* counts, int64_t items_stride, int64_t scores_stride,
+             int64_t counts_stride, int64_t* out_items, float* out_scores, int32_t* out_counts) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+    __shared__ int s_cnt;
+    __shared__ uint64_t s_admit;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int cap = 1 << (32 - __clz(k + kSelectThreads - 1));
+    if (tid == 0) {
+        s_cnt = 0;
+        s_admit = 0;
+    }
+    CandList l{keys, &s_cnt, &s_admit};
+    const int64_t total = static_cast<int64_t>(n_lists) * k;
+    int need = 0;
+    for (int64_t base = 0; base < total; base += kSelectThreads) {
+        if (__syncthreads_or(need)) {
+            need = 0;
+            list_compact<kSelectThreads>(l, cap, k, 0);
+        }
+        const int64_t i = base + tid;
+        if (i < total) {
+            const int g = static_cast<int>(i / k), j = static_cast<int>(i % k);
+            if (j < counts[g * counts_stride + q]) {
+                const float sc = scores[g * scores_stride + static_cast<size_t>(q) * k + j];
+                const uint64_t key = make_key(sc, static_cast<uint32_t>(g * k + (k - 1 - j)));
+                if (key >= s_admit) need |= list_push(l, key, cap - kSelectThreads);
+            }
+        }
+    }
+    __syncthreads();
+    list_compact<kSelectThreads>(l, cap, k, 0);
+    const int n = s_cnt;
+    for (int j = tid; j < k; j += kSelectThreads) {
+        int64_t item = -1;
+        float sc = 0.0f;
+        if (j < n) {
+            const uint32_t low = key_pos(keys[j]);
+            const int g = low / k, jj = k - 1 - static_cast<int>(low % k);
+            item = items[g * items_stride + static_cast<size_t>(q) * k + jj];
+            sc = key_score(keys[j]);
+        }
+        out_items[static_cast<size_t>(q) * k + j] = item;
+        out_scores[static_cast<size_t>(q) * k + j] = sc;
+    }
+    if (tid == 0) out_counts[q] = n;
+}
+
+cudaError_t launch_merge(int n_lists, int n_queries, int k, const int64_t* items,
+                         const float* scores, const int32_t* counts, int64_t items_stride,
+                         int64_t scores_stride, int64_t counts_stride, int64_t* out_items,
+                         float* out_scores, int32_t* out_counts, cudaStream_t s) {
+    if (items_stride == 0) items_stride = static_cast<int64_t>(n_queries) * k;
+    if (scores_stride == 0) scores_stride = static_cast<int64_t>(n_queries) * k;
+    if (counts_stride == 0) counts_stride = n_queries;
+    const size_t smem = static_cast<size_t>(select_cap(k)) * sizeof(uint64_t);
+    cudaError_t e = cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    merge_kernel<<<n_queries, kSelectThreads, smem, s>>>(n_lists, n_queries, k, items, scores,
+                                                         counts, items_stride, scores_stride,
+                                                         counts_stride, out_items, out_scores,
+                                                         out_counts);
+    return cudaGetLastError();
+}
+
+// ---- convert-on-append (fused optional L2 normalisation) ---------------------------------
+template <typename S, typename D>
+__device__ __forceinline__ D convert_elem(S v);
+template <> __device__ __forceinline__ float convert_elem<float, float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 convert_elem<float, __nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half convert_elem<float, __half>(float v) { return __float2half_rn(v); }
+
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) convert_rows_kernel(const S* src, D* dst, int64_t n, int dim,
+                                                          int normalize) {
+    // one warp per row
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t row = warp; row < n; row += n_warps) {
+        const S* s = src + row * dim;
+        D* d = dst + row * dim;
+        float inv = 1.0f;
+        if (normalize) {
+            float ss = 0.0f;
+            for (int c = lane; c < dim; c += 32) {
+                const float v = to_float(s[c]);
+                ss = fmaf(v, v, ss);
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
+            const float nrm = sqrtf(ss);
+            inv = nrm > 0.0f ? nrm : 1.0f;  // the divisor; zero rows stay zero (model_adapters.py:182)
+        }
+        for (int c = lane; c < dim; c += 32) {
+            float v = to_float(s[c]);
+            if (normalize) v = v / inv;
+            d[c] = convert_elem<float, D>(v);
+        }
+    }
+}
+
+template <typename S>
+static cudaError_t launch_convert_s(const S* src, void* dst, int dst_dtype, int64_t n, int dim,
+                                    int normalize, cudaStream_t s) {
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    const int g = static_cast<int>(blocks);
+    switch (dst_dtype) {
+        case TAV_F32: convert_rows_kernel<S, float><<<g, 256, 0, s>>>(src, static_cast<float*>(dst), n, dim, normalize); break;
+        case TAV_BF16: convert_rows_kernel<S, __nv_bfloat16><<<g, 256, 0, s>>>(src, static_cast<__nv_bfloat16*>(dst), n, dim, normalize); break;
+        case TAV_F16: convert_rows_kernel<S, __half><<<g, 256, 0, s>>>(src, static_cast<__half*>(dst), n, dim, normalize); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_convert(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
+                           int dim, int normalize, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    switch (src_dtype) {
+        case TAV_F32: return launch_convert_s(static_cast<const float*>(src), dst, dst_dtype, n, dim, normalize, s);
+        case TAV_BF16: return launch_convert_s(static_cast<const __nv_bfloat16*>(src), dst, dst_dtype, n, dim, normalize, s);
+        case TAV_F16: return launch_convert_s(static_cast<const __half*>(src), dst, dst_dtype, n, dim, normalize, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace tav
