@@ -18,9 +18,10 @@
  * every compute entry point fails with TAV_ERR_CUDA.
  *
  * Threading: an index may be used from one thread at a time.  Work is enqueued on the
- * caller's stream (`stream`, a cudaStream_t passed as void*; NULL = the index's own
- * stream).  Entry points that take host output pointers synchronise that stream before
- * returning; with TAV_OUTPUTS_ON_DEVICE they return as soon as the work is enqueued.
+ * caller's stream (`stream`, a cudaStream_t passed as void*; NULL = the CUDA legacy default
+ * stream, as everywhere in the CUDA runtime).  Entry points that take host output pointers
+ * synchronise that stream before returning; with TAV_OUTPUTS_ON_DEVICE they return as soon
+ * as the work is enqueued, ordered after earlier work on the same stream.
  */
 #ifndef TAVEC_H
 #define TAVEC_H
@@ -33,7 +34,7 @@ extern "C" {
 
 #define TAV_ABI_VERSION 1
 
-typedef struct tav_index tav_index; /* opaque: device corpus + workspace + stream */
+typedef struct tav_index tav_index; /* opaque: device corpus + search workspace */
 
 /* storage / source element types */
 enum tav_dtype { TAV_F32 = 0, TAV_BF16 = 1, TAV_F16 = 2 };
@@ -131,6 +132,12 @@ int tav_merge_topk(int device, int n_lists, int n_queries, int k, const int64_t*
                    const float* scores, const int32_t* counts, int64_t items_stride,
                    int64_t scores_stride, int64_t counts_stride, int64_t* out_items,
                    float* out_scores, int32_t* out_counts, void* stream);
+
+/* Verification aid for the tensor-core path: every raw dot product it computes,
+ * out_device[n_queries, size] float32 (device memory), for bf16/fp16 indexes.  `flags` may
+ * carry TAV_QUERIES_ON_DEVICE.  Synchronises.  Not a hot-path entry point. */
+int tav_mma_scores(tav_index* ix, const float* queries, int n_queries, int flags, float* out_device,
+                   void* stream);
 
 /* Device time of the last tav_search on this index, measured with CUDA events on the
  * search's stream: `scan_ms` = the dominant kernel(s) (row scan or MMA kernel, summed over

@@ -1,0 +1,133 @@
+"""The tcgen05 tensor-core path (bf16 / fp16 storage, batched queries) against the oracle.
+
+Inputs are rounded to the storage dtype first ("identical fp32 inputs": the oracle gets the
+rounded values upcast to float32), so products are exact in float32 and only the summation
+order differs between the tensor core and OpenBLAS: scores agree to ~1e-6, index sets up to
+ties at that level (tests/parity.py).
+  * raw GEMM check: every dot product the kernel computes (tav_mma_scores) vs float64;
+  * search parity vs the oracle, with and without the sampled admission threshold;
+  * row-scan kernel vs tensor-core kernel on the same data (two independent CUDA paths);
+  * the exact-fallback: score distributions that defeat the sampled threshold.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import typeagent_py_b200 as tab
+from oracle import vectorbase_oracle as O
+from tests.parity import assert_hits_match
+from typeagent_py_b200 import _capi
+
+pytestmark = pytest.mark.gpu
+
+
+def make_base(v, storage, path="mma"):
+    base = tab.VectorBase(tab.TextEmbeddingIndexSettings(O.FakeEmbeddingModel()), storage_dtype=storage)
+    base.add_embeddings(None, v)
+    base.force_path = path
+    return base
+
+
+def mma_scores(base, q):
+    import torch
+
+    lib, ix = base._ensure_device()
+    out = torch.empty((len(q), len(base)), dtype=torch.float32, device="cuda")
+    q = np.ascontiguousarray(q, np.float32)
+    _capi.check(lib.tav_mma_scores(ix, q.ctypes.data_as(C.c_void_p), len(q), 0,
+                                   C.c_void_p(out.data_ptr()), None))
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("storage", ["bfloat16", "float16"])
+@pytest.mark.parametrize("n,d,b", [(256, 64, 128), (1000, 768, 5), (3001, 136, 130), (700, 1536, 256),
+                                    (513, 8, 300), (40000, 384, 64)])
+def test_every_dot_product_of_the_tensor_core_path(storage, n, d, b):
+    v, q = O.make_corpus(n, d, seed=n + d, n_queries=b)
+    vr, qr = O.round_to_storage(v, storage), O.round_to_storage(q, storage)
+    base = make_base(v, storage)
+    got = mma_scores(base, q)
+    want = qr.astype(np.float64) @ vr.astype(np.float64).T
+    assert got.shape == want.shape
+    # fp32 accumulation of exact products: error ~ sqrt(d) * 2^-24 * |x|; bound generously
+    np.testing.assert_allclose(got, want, atol=2e-6, rtol=0)
+
+
+@pytest.mark.parametrize("storage,n,d,b,k,ms", [
+    ("bfloat16", 20000, 768, 64, 32, 0.0),      # sampled threshold
+    ("bfloat16", 50000, 384, 300, 5, 0.0),      # two query chunks (256 + 44), RelatedTerms shape
+    ("float16", 30000, 1536, 17, 100, 0.0),
+    ("bfloat16", 4000, 128, 200, 10, 0.0),      # small corpus: no sampling, floor threshold
+    ("float16", 20011, 256, 33, 50, 0.52),      # min_score above the sampled threshold for some
+    ("bfloat16", 16385, 64, 256, 2048, 0.0),    # k = pass limit
+    ("bfloat16", 100000, 64, 8, 10, 0.0),
+])
+def test_search_matches_oracle(storage, n, d, b, k, ms):
+    v, q = O.make_corpus(n, d, seed=n + b, n_queries=b)
+    vr, qr = O.round_to_storage(v, storage), O.round_to_storage(q, storage)
+    base = make_base(v, storage)
+    batch = base.fuzzy_lookup_embeddings(qr, max_hits=k, min_score=ms)
+    assert base.last_timing()["path"] == "mma"
+    for i in list(range(min(b, 12))) + [b - 1]:
+        assert_hits_match(batch[i], O.lookup(vr, qr[i], k, ms), min_score=ms, what=f"{storage} q{i}")
+
+
+def test_unrounded_float32_queries_are_rounded_like_the_corpus():
+    v, q = O.make_corpus(20000, 256, seed=5, n_queries=20)
+    base = make_base(v, "bfloat16")
+    vr, qr = O.round_to_bfloat16(v), O.round_to_bfloat16(q)
+    for got, qq in zip(base.fuzzy_lookup_embeddings(q, 10, 0.0), qr):
+        assert_hits_match(got, O.lookup(vr, qq, 10, 0.0))
+
+
+def test_scan_and_mma_paths_agree():
+    v, q = O.make_corpus(60000, 512, seed=77, n_queries=40)
+    qr = O.round_to_bfloat16(q)
+    a = make_base(v, "bfloat16", "mma").search_arrays(qr, 64, 0.0)
+    b = make_base(v, "bfloat16", "scan").search_arrays(qr, 64, 0.0)
+    np.testing.assert_array_equal(a[2], b[2])
+    for i in range(len(qr)):
+        assert_hits_match({"items": a[0][i].tolist(), "scores": a[1][i].tolist()},
+                          {"items": b[0][i].tolist(), "scores": b[1][i].tolist()}, score_tol=2e-6)
+
+
+def test_auto_path_selection():
+    v, q = O.make_corpus(20000, 128, seed=3, n_queries=32)
+    base = make_base(v, "bfloat16", None)
+    base.fuzzy_lookup_embeddings(q, 5, 0.0)
+    assert base.last_timing()["path"] == "mma"
+    base.fuzzy_lookup_embedding(q[0], 5, 0.0)
+    assert base.last_timing()["path"] == "scan"
+    f32 = make_base(v, "float32", None)
+    f32.fuzzy_lookup_embeddings(q, 5, 0.0)
+    assert f32.last_timing()["path"] == "scan"
+    with pytest.raises(ValueError):
+        bad = make_base(v, "float32", "mma")
+        bad.fuzzy_lookup_embeddings(q, 5, 0.0)
+
+
+def test_fallback_when_the_sampled_threshold_cannot_decide():
+    """(a) 30000 identical rows: every score ties -> all rows admitted -> candidate overflow;
+    (b) the best rows hide in one unsampled tile and everything else scores far lower:
+    the threshold from the sample is fine (admits them) — but a corpus whose sampled tiles are
+    all high-scoring and the rest low starves the admission.  Both must still be exact."""
+    row = O.round_to_bfloat16(O.make_corpus(1, 64, seed=9)[0])
+    same = np.repeat(row, 30000, axis=0)
+    base = make_base(same, "bfloat16")
+    got = base.fuzzy_lookup_embeddings(np.repeat(row, 3, axis=0), 7, 0.0)
+    for hits in got:
+        assert [h.item for h in hits] == list(range(29999, 29992, -1))
+    # starvation: tile 0 is sampled and holds near-duplicates of the query; nothing else comes close
+    v, q = O.make_corpus(40000, 64, seed=10, n_queries=2)
+    v = v.copy()
+    v[:256] = q[0] + 0.01 * v[:256]
+    v[:256] /= np.linalg.norm(v[:256], axis=1, keepdims=True)
+    vr, qr = O.round_to_bfloat16(v), O.round_to_bfloat16(q)
+    base = make_base(v, "bfloat16")
+    got = base.fuzzy_lookup_embeddings(qr, 400, 0.0)
+    for hits, qq in zip(got, qr):
+        assert_hits_match(hits, O.lookup(vr, qq, 400, 0.0))

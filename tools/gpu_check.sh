@@ -1,0 +1,32 @@
+#!/bin/bash
+# One gpurun call: GPU tests, smoke, small benches; everything lands in gpurun_out/.
+# usage: gpurun --timeout 1500 -- 'bash tools/gpu_check.sh [stage ...]'
+set -u
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+stages="${*:-info tests smoke bench_c1 bench_c3}"
+for st in $stages; do
+  echo "=== stage $st ($(date +%T))"
+  case $st in
+    info)
+      nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total,power.limit --format=csv > gpurun_out/gpu_info.txt 2>&1
+      nproc >> gpurun_out/gpu_info.txt; free -g >> gpurun_out/gpu_info.txt ;;
+    tests)
+      timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.log ;;
+    smoke)
+      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -20 | tee gpurun_out/smoke.log ;;
+    bench_c1)
+      timeout 300 python bench.py --workload c1 --steps 50 --warmup 10 2>gpurun_out/bench_c1.err | tee gpurun_out/bench_c1.json ;;
+    bench_c2)
+      timeout 600 python bench.py --workload c2 --steps 10 --warmup 3 2>gpurun_out/bench_c2.err | tee gpurun_out/bench_c2.json ;;
+    bench_c3)
+      timeout 900 python bench.py --steps 5 --warmup 3 2>gpurun_out/bench_c3.err | tee gpurun_out/bench_c3.json ;;
+    bench_c5)
+      timeout 600 python bench.py --workload c5 --steps 10 --warmup 3 2>gpurun_out/bench_c5.err | tee gpurun_out/bench_c5.json ;;
+    ncu_c1)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
+        --log-file gpurun_out/launches_c1.csv python bench.py --workload c1 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_c1.log 2>&1 ;;
+    *) echo "unknown stage $st" ;;
+  esac
+done
+echo "=== done ($(date +%T))"

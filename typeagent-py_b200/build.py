@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtavec.so")
 STAMP = os.path.join(HERE, ".libtavec.stamp")
 SOURCES = ["tav_api.cu", "tav_scan.cu", "tav_mma.cu"]
-HEADERS = ["tav_common.cuh", "tav_internal.h", "../../include/tavec.h"]
+HEADERS = ["tav_common.cuh", "tav_internal.h", "tav_ptx.cuh", "../../include/tavec.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

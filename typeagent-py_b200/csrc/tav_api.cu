@@ -77,7 +77,6 @@ struct tav_index {
     int64_t capacity = 0;
     void* rows = nullptr;  // [capacity, dim] storage dtype
     bool adopted = false;
-    cudaStream_t own_stream = nullptr;
 
     // search workspace
     DevBuf queries;     // float32 [n_queries, dim]
@@ -147,8 +146,7 @@ int tav_create(int device, int dim, int store_dtype, int index_flags, int64_t re
     ix->dtype = store_dtype;
     ix->flags = index_flags;
     for (auto& pr : ix->ev_chunk) pr[0] = pr[1] = nullptr;
-    cudaError_t ce = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
-    if (ce == cudaSuccess) ce = cudaEventCreate(&ix->ev_total[0]);
+    cudaError_t ce = cudaEventCreate(&ix->ev_total[0]);
     if (ce == cudaSuccess) ce = cudaEventCreate(&ix->ev_total[1]);
     for (int i = 0; ce == cudaSuccess && i < kMaxTimedChunks; ++i) {
         ce = cudaEventCreate(&ix->ev_chunk[i][0]);
@@ -174,7 +172,7 @@ int tav_create(int device, int dim, int store_dtype, int index_flags, int64_t re
 int tav_destroy(tav_index* ix) {
     if (!ix) return TAV_OK;
     cudaSetDevice(ix->device);
-    if (ix->own_stream) cudaStreamSynchronize(ix->own_stream);
+    cudaDeviceSynchronize();  // searches may still be in flight on the caller's streams
     if (ix->rows && !ix->adopted) cudaFree(ix->rows);
     for (DevBuf* b : {&ix->queries, &ix->subset, &ix->cand_keys, &ix->cand_count, &ix->out_items,
                       &ix->out_scores, &ix->out_counts, &ix->staging, &ix->mma_ws, &ix->retry})
@@ -184,7 +182,6 @@ int tav_destroy(tav_index* ix) {
     for (auto& pr : ix->ev_chunk)
         for (auto& ev : pr)
             if (ev) cudaEventDestroy(ev);
-    if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
     delete ix;
     return TAV_OK;
 }
@@ -251,7 +248,7 @@ int tav_append(tav_index* ix, const void* rows, int64_t n, int dim, int src_dtyp
     }
     if (n == 0) return TAV_OK;
     if (int rc = set_device(ix)) return rc;
-    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ix->own_stream;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (ix->size + n > ix->capacity) {
         int64_t want = std::max<int64_t>(ix->size + n, ix->capacity * 2);
         want = std::max<int64_t>(want, 1024);
@@ -326,7 +323,7 @@ int tav_read_rows(tav_index* ix, int64_t first, int64_t n, float* out_host, void
     }
     if (n == 0) return TAV_OK;
     if (int rc = set_device(ix)) return rc;
-    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ix->own_stream;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t row = static_cast<size_t>(ix->dim) * dtype_size(ix->dtype);
     const char* src = static_cast<const char*>(ix->rows) + static_cast<size_t>(first) * row;
     if (ix->dtype == TAV_F32) {
@@ -424,7 +421,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
     }
     if (n_queries == 0) return TAV_OK;
     if (int rc = set_device(ix)) return rc;
-    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ix->own_stream;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool q_dev = flags & TAV_QUERIES_ON_DEVICE, o_dev = flags & TAV_OUTPUTS_ON_DEVICE;
     const size_t nk = static_cast<size_t>(n_queries) * k;
 
@@ -526,13 +523,15 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
         m.out_counts = d_counts;
         TAV_CUDA(ix->retry.ensure(static_cast<size_t>(n_queries) * sizeof(int32_t)));
         m.retry_flags = static_cast<int32_t*>(ix->retry.p);
-        m.ev_main_begin = ix->ev_chunk[0][0];
-        m.ev_main_end = ix->ev_chunk[0][1];
+        m.ev = ix->ev_chunk;
+        m.ev_max = kMaxTimedChunks;
+        int ev_used = 0;
+        m.ev_used = &ev_used;
         const size_t ws = mma_workspace_bytes(m);
         TAV_CUDA(ix->mma_ws.ensure(ws));
         int launches = 0;
         TAV_CUDA(launch_mma_search(m, ix->mma_ws.p, ws, s, &launches));
-        ix->timed_chunks = 1;
+        ix->timed_chunks = ev_used;
         ix->launches += launches;
         // Queries the sampled admission threshold could not settle (fewer than k admitted rows
         // although rows were cut, or candidate overflow) are redone exactly by the row scan.
@@ -563,6 +562,38 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
                                  cudaMemcpyDeviceToHost, s));
         TAV_CUDA(cudaStreamSynchronize(s));
     }
+    return TAV_OK;
+}
+
+int tav_mma_scores(tav_index* ix, const float* queries, int n_queries, int flags, float* out_device,
+                   void* stream) {
+    if (!ix || n_queries < 1 || !queries || !out_device) return TAV_ERR_INVALID;
+    if (!mma_supported(ix->dtype, ix->dim) || ix->size == 0) {
+        set_error("tav_mma_scores: needs a non-empty bf16/fp16 index with dim %% 8 == 0");
+        return TAV_ERR_INVALID;
+    }
+    if (int rc = set_device(ix)) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const float* d_queries = queries;
+    if (!(flags & TAV_QUERIES_ON_DEVICE)) {
+        const size_t q_bytes = static_cast<size_t>(n_queries) * ix->dim * sizeof(float);
+        TAV_CUDA(ix->queries.ensure(q_bytes));
+        TAV_CUDA(cudaMemcpyAsync(ix->queries.p, queries, q_bytes, cudaMemcpyHostToDevice, s));
+        d_queries = static_cast<const float*>(ix->queries.p);
+    }
+    MmaArgs m{};
+    m.device = ix->device;
+    m.corpus = ix->rows;
+    m.dtype = ix->dtype;
+    m.n_corpus = ix->size;
+    m.dim = ix->dim;
+    m.queries = d_queries;
+    m.nq = n_queries;
+    m.k = 1;
+    const size_t ws = mma_workspace_bytes(m);
+    TAV_CUDA(ix->mma_ws.ensure(ws));
+    TAV_CUDA(launch_mma_dump(m, ix->mma_ws.p, ws, out_device, s));
+    TAV_CUDA(cudaStreamSynchronize(s));
     return TAV_OK;
 }
 

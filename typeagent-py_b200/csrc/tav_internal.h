@@ -76,11 +76,16 @@ struct MmaArgs {
     float* out_scores;
     int32_t* out_counts;
     int32_t* retry_flags;  // device [nq]: set to 1 for queries the caller must redo with the row scan
-    cudaEvent_t ev_main_begin, ev_main_end;  // recorded around the dominant kernel (may be null)
+    cudaEvent_t (*ev)[2];  // optional event pairs, one recorded around each 256-query chunk's
+    int ev_max;            //   sample + threshold + main kernels
+    int* ev_used;
 };
 size_t mma_workspace_bytes(const MmaArgs& a);
 cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspace_bytes,
                               cudaStream_t s, int* launches);
+// verification aid: every raw dot product of the tensor-core path, out[nq, n_corpus] on the device
+cudaError_t launch_mma_dump(const MmaArgs& a, void* workspace, size_t workspace_bytes, float* out,
+                            cudaStream_t s);
 
 void set_error(const char* fmt, ...);
 

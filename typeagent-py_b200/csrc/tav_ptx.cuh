@@ -1,0 +1,153 @@
+// tav_ptx.cuh — thin inline-PTX wrappers for the Blackwell (sm_100a) async machinery used by
+// tav_mma.cu: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld / fences).
+// Encodings of the shared-memory and instruction descriptors follow the PTX ISA tables (cross-
+// checked against the CUTLASS 4.x cute/arch/mma_sm100_desc.hpp bit-fields vendored in this image).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tav {
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xFFFFFFFF;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// ---- mbarrier ------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// Blocks until the phase with `parity` completes.  A pipeline bug would otherwise hang the GPU
+// forever; after ~4e9 cycles (seconds) of waiting the kernel traps instead.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+
+// ---- TMA -----------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// L2 eviction-priority policies (createpolicy encodings used by CUTLASS' TMA::CacheHintSm90)
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+
+// 2-D tiled load: box at (c0 = innermost coordinate, c1 = row) -> smem, completes on `bar`
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0,
+                                            int32_t c1, uint64_t cache_hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "l"(cache_hint)
+        : "memory");
+}
+
+// ---- tcgen05 -------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// whole-warp: allocate `cols` (power of two >= 32) TMEM columns, base address written to *smem_slot
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; single thread issues on behalf of the CTA
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (base_lane + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- descriptors ---------------------------------------------------------------------------
+// K-major operand tile in the 128-byte-swizzle canonical layout (what TMA SWIZZLE_128B writes
+// for a box of 64 16-bit elements x rows): rows are 128 B apart, 8-row groups 1024 B apart.
+//   bits [0,14)  start address >> 4         bits [16,30) leading byte offset >> 4 (unused for SW128 K-major: 1)
+//   bits [32,46) stride byte offset >> 4    bits [46,48) descriptor version = 1 (Blackwell)
+//   bits [61,64) layout type: 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+// kind::f16 instruction descriptor: D = F32, A/B = BF16 (1) or F16 (0), both K-major, dense.
+//   [4,6) D format (1 = F32)  [7,10) A format  [10,13) B format  [15] A major  [16] B major
+//   [17,23) N >> 3            [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int ab_format) {
+    return (1u << 4) | (static_cast<uint32_t>(ab_format) << 7) | (static_cast<uint32_t>(ab_format) << 10) |
+           (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+}  // namespace ptx
+}  // namespace tav
