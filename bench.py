@@ -168,55 +168,83 @@ def workload_config(args, w, n_gpus):
 
 # ----------------------------------------------------------------------------- GPU side
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / power / throttle reasons sampled every few ms DURING the timed region
+    (NVML in a thread; falls back to polling nvidia-smi)."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, gpu_index: int):
-        self.rows = []
-        self.proc = None
+    def __init__(self, gpu_index: int, period_s: float = 0.004):
+        self.samples = []  # (sm_mhz, power_w, reasons_bitmask)
+        self.sm_max = None
+        self.period = period_s
+        self._stop = threading.Event()
+        self.source = "nvml"
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML enumerates physical order; honour CUDA_VISIBLE_DEVICES when it is a plain list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[gpu_index])
+                except Exception:
+                    phys = gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._loop_nvml, daemon=True)
+        except Exception:
+            self.nv = None
+            self.source = "nvidia-smi"
+            self.gpu_index = gpu_index
+            self.thread = threading.Thread(target=self._loop_smi, daemon=True)
+        self.thread.start()
+
+    def _loop_nvml(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def _loop_smi(self):
+        fields = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={fields}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                parts = [p.strip() for p in out.stdout.strip().split(",")]
+                self.sm_max = float(parts[1])
+                self.samples.append((float(parts[0]), float(parts[2]), int(parts[3], 16)))
+            except Exception:
+                pass
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
-            parts = [p.strip() for p in row.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0])), smax.append(float(parts[1])), power.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        busy = [s for s, p in zip(sm, power) if p > 250] or sm
-        return {"sm_mhz": statistics.median(busy) if busy else None,
-                "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        self.thread.join(timeout=5)
+        # NVML clocks-event reason bits
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+        sm = [s for s, _, _ in self.samples]
+        pw = [p for _, p, _ in self.samples]
+        mask = 0
+        for _, _, r in self.samples:
+            mask |= r
+        reasons = sorted(n for bit, n in names.items() if mask & bit)
+        # "under load": samples whose power is within 25% of the run's maximum
+        pmax = max(pw) if pw else 0.0
+        busy = [s for s, p in zip(sm, pw) if p >= 0.75 * pmax] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_min_mhz": min(busy) if busy else None,
+                "sm_max_mhz": self.sm_max, "power_w_max": pmax if pw else None, "samples": len(sm),
+                "source": self.source, "reasons": reasons}
 
 
 def make_shard_on_device(torch, device, lo, hi, dim, storage, seed):

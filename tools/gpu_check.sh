@@ -20,12 +20,20 @@ for st in $stages; do
     bench_c2)
       timeout 600 python bench.py --workload c2 --steps 10 --warmup 3 2>gpurun_out/bench_c2.err | tee gpurun_out/bench_c2.json ;;
     bench_c3)
-      timeout 900 python bench.py --steps 5 --warmup 3 2>gpurun_out/bench_c3.err | tee gpurun_out/bench_c3.json ;;
+      timeout 900 python bench.py --steps 40 --warmup 5 2>gpurun_out/bench_c3.err | tee gpurun_out/bench_c3.json ;;
+    tests_mma)
+      timeout 600 python -m pytest tests/test_gpu_mma.py -m gpu -x -q 2>&1 | tail -40 | tee gpurun_out/pytest_mma.log ;;
     bench_c5)
       timeout 600 python bench.py --workload c5 --steps 10 --warmup 3 2>gpurun_out/bench_c5.err | tee gpurun_out/bench_c5.json ;;
     ncu_c1)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
         --log-file gpurun_out/launches_c1.csv python bench.py --workload c1 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_c1.log 2>&1 ;;
+    ncu_c3_list)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv \
+        --log-file gpurun_out/launches_c3.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_c3_list.log 2>&1 ;;
+    ncu_c3_full)
+      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:mma_topk -s 3 -c 1 \
+        -o gpurun_out/prof_c3 -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_c3_full.log 2>&1 ;;
     *) echo "unknown stage $st" ;;
   esac
 done

@@ -7,17 +7,19 @@
 // values are exact in float32, so on storage-rounded inputs only the summation order differs
 // from the reference's sgemv.
 //
-// Shape of one CTA (persistent, one per SM, 192 threads):
+// Shape of one CTA (persistent, one per SM, 320 threads):
 //   warp 0     TMA producer: per (corpus tile, query block, 64-wide K slice) loads the query
 //              slice [128 x 64] and the corpus slice [256 x 64] into a 4-stage smem ring
 //              (128-byte swizzle), completing on an mbarrier.
 //   warp 1     MMA issuer: one elected thread issues tcgen05.mma.kind::f16 M=128 N=256 K=16
 //              (4 per stage), accumulating into one of two 256-column TMEM stages;
 //              tcgen05.commit frees the smem slot / publishes the accumulator.
-//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns — a thread owns ONE query (its TMEM
-//              lane) and walks that query's scores for the tile's 256 rows: one compare per
-//              element against the query's admission threshold; admitted (dot, row) pairs go to
-//              the query's global candidate buffer.  Overlaps the next tile's MMAs.
+//   warps 2-9  epilogue: tcgen05.ld 32 lanes x 32 columns, double-buffered in registers — a
+//              thread owns ONE query (its TMEM lane) and half of the tile's 256 rows.  Per
+//              32-row chunk it takes the max of the 32 dots (branch-free) and compares it with
+//              the query's admission threshold; only chunks that contain an admitted row take
+//              the slow path that appends (dot, row) pairs to the query's global candidate
+//              buffer.  Runs concurrently with the next tile's MMAs (two TMEM stages).
 //
 // Admission thresholds.  A first launch of the same kernel in SAMPLE mode scores a strided
 // sample of corpus tiles and keeps, per query, the 16 largest dots in registers; a tiny kernel
@@ -53,12 +55,14 @@ constexpr int kStages = 4;
 constexpr int kABytes = kBM * kBK * 2;              // 16 KB
 constexpr int kBBytes = kBN * kBK * 2;              // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;      // 48 KB
-constexpr int kMmaThreads = 192;
+constexpr int kEpiWarps = 8;                        // 4 TMEM lane quadrants x 2 column halves
+constexpr int kMmaThreads = 64 + 32 * kEpiWarps;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiCols = kBN / 2;                   // columns per epilogue warp
 constexpr int kMaxMT = 2;                           // query blocks per launch (2 x 128 queries)
 constexpr int kChunkQueries = kBM * kMaxMT;         // 256
 constexpr int kSampleTop = 16;
 constexpr int kTmemCols = 512;
-constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(kStages) * kStageBytes + 256;
+constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(kStages) * kStageBytes + 256;  // both forms: 192 KB of tiles
 
 enum Mode { kSample = 0, kMain = 1, kDump = 2 };
 
@@ -71,7 +75,7 @@ struct KernelArgs {
     int nq;                // valid queries in this chunk (<= 256)
     int mt;                // query blocks (1 or 2)
     const float* thr;      // MAIN: [256] admission threshold (raw dot) per query
-    float* sample_top;     // SAMPLE: [gridDim.x, 256, 16]
+    float* sample_top;     // SAMPLE: [units, 2 column halves, 256, 16]
     uint64_t* cand;        // MAIN: [256, capg]  (dot bits << 32 | row)
     uint32_t* cand_count;  // MAIN: [256]
     uint32_t capg;
@@ -88,56 +92,84 @@ __device__ __forceinline__ void insert_top16(float (&top)[kSampleTop], float x) 
     }
 }
 
-template <int MODE>
+// CG = 1: one CTA per tile, up to 2 query blocks processed one after the other.
+// CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per tile: CTA r owns query block r
+//         (its 128 TMEM lanes) and stages rows [128r, 128r+128) of the corpus tile; every MMA is
+//         M=256 x N=256 across the pair, so each CTA's shared memory sees half of the operand
+//         traffic of the single-CTA form — the single-CTA form is smem-bandwidth bound at ~55 %
+//         of the tensor pipe (profiles/README.md).
+template <int MODE, int CG>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                 const KernelArgs a, const uint32_t idesc) {
+    constexpr int kRowsB = kBN / CG;                         // corpus rows staged per CTA per tile
+    constexpr int kStageBytesCta = kABytes + kRowsB * kBK * 2;
+    constexpr int kNumStages = CG == 2 ? 6 : 4;              // 6 x 32 KB or 4 x 48 KB
     extern __shared__ uint8_t smem_dyn[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(kStages) * kStageBytes);
-    uint64_t* full = bars;                 // [kStages] TMA -> MMA
-    uint64_t* empty = bars + kStages;      // [kStages] MMA -> TMA
-    uint64_t* tfull = bars + 2 * kStages;  // [2] MMA -> epilogue
-    uint64_t* tempty = tfull + 2;          // [2] epilogue -> MMA
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(kNumStages) * kStageBytesCta);
+    uint64_t* full = bars;                    // [stages] TMA -> MMA      (the leader's copy is used)
+    uint64_t* empty = bars + kNumStages;      // [stages] MMA -> TMA      (each CTA its own)
+    uint64_t* tfull = bars + 2 * kNumStages;  // [2] MMA -> epilogue      (each CTA its own)
+    uint64_t* tempty = tfull + 2;             // [2] epilogue -> MMA      (the leader's copy is used)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0;
+    const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;  // a unit = CTA or CTA pair
+    const int n_mblocks = CG == 2 ? 1 : a.mt;                    // query blocks this CTA walks per tile
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            ptx::mbar_init(&full[s], 1);
+        for (int s = 0; s < kNumStages; ++s) {
+            ptx::mbar_init(&full[s], 1);      // the leader's producer arrives once with the unit's bytes
             ptx::mbar_init(&empty[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tfull[s], 1);
-            ptx::mbar_init(&tempty[s], 4);  // one arrive per epilogue warp
+            ptx::mbar_init(&tempty[s], kEpiWarps * CG);  // one arrive per epilogue warp of the unit
         }
         ptx::fence_mbar_init();
         ptx::prefetch_tensormap(&map_q);
         ptx::prefetch_tensormap(&map_c);
     }
-    if (warp == 1) ptx::tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == 1) {
+        if (CG == 2) ptx::tmem_alloc_pair(tmem_slot, kTmemCols);
+        else ptx::tmem_alloc(tmem_slot, kTmemCols);
+    }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CG == 2) ptx::cluster_sync_all();
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer (every CTA) =================
         if (ptx::elect_one()) {
             uint32_t stage = 0, phase = 0;
-            for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
+            for (int w = unit; w < a.n_work; w += n_units) {
                 const int64_t tile = (static_cast<int64_t>(w) * a.tile_mul) / a.tile_div;
-                const int32_t row0 = static_cast<int32_t>(tile * kBN);
-                for (int m = 0; m < a.mt; ++m) {
+                const int32_t row0 = static_cast<int32_t>(tile * kBN + cta_rank * kRowsB);
+                for (int mb = 0; mb < n_mblocks; ++mb) {
+                    const int m = CG == 2 ? static_cast<int>(cta_rank) : mb;
                     for (int kb = 0; kb < a.kb_count; ++kb) {
                         ptx::mbar_wait(&empty[stage], phase ^ 1);
-                        uint8_t* sa = tiles + static_cast<size_t>(stage) * kStageBytes;
-                        ptx::mbar_expect_tx(&full[stage], kStageBytes);
-                        ptx::tma_load_2d(sa, &map_q, &full[stage], kb * kBK, m * kBM, ptx::kEvictLast);
-                        ptx::tma_load_2d(sa + kABytes, &map_c, &full[stage], kb * kBK, row0, ptx::kEvictFirst);
-                        if (++stage == kStages) {
+                        uint8_t* sa = tiles + static_cast<size_t>(stage) * kStageBytesCta;
+                        if (CG == 2) {
+                            // Both CTAs' loads complete on the LEADER's barrier; only the leader arms it,
+                            // with the bytes of both (a peer load landing first just drives the pending
+                            // byte count negative until the leader's expect_tx; the peer cannot run a phase
+                            // ahead because its slot is released by the same multicast commit).
+                            const uint32_t lead_full = ptx::map_to_cta(ptx::smem_u32(&full[stage]), 0);
+                            if (cta_rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * kStageBytesCta);
+                            ptx::tma_load_2d_pair(sa, &map_q, lead_full, kb * kBK, m * kBM, ptx::kEvictLast);
+                            ptx::tma_load_2d_pair(sa + kABytes, &map_c, lead_full, kb * kBK, row0, ptx::kEvictFirst);
+                        } else {
+                            ptx::mbar_expect_tx(&full[stage], kStageBytesCta);
+                            ptx::tma_load_2d(sa, &map_q, &full[stage], kb * kBK, m * kBM, ptx::kEvictLast);
+                            ptx::tma_load_2d(sa + kABytes, &map_c, &full[stage], kb * kBK, row0, ptx::kEvictFirst);
+                        }
+                        if (++stage == kNumStages) {
                             stage = 0;
                             phase ^= 1;
                         }
@@ -146,121 +178,163 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (ptx::elect_one()) {
+        // ================= MMA issuer (leader CTA of the unit) =================
+        if (cta_rank == 0 && ptx::elect_one()) {
             uint32_t stage = 0, phase = 0, item = 0;
-            for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
-                for (int m = 0; m < a.mt; ++m, ++item) {
+            for (int w = unit; w < a.n_work; w += n_units) {
+                for (int mb = 0; mb < n_mblocks; ++mb, ++item) {
                     const uint32_t as = item & 1, aphase = (item >> 1) & 1;
-                    ptx::mbar_wait(&tempty[as], aphase ^ 1);  // epilogue drained this accumulator
+                    ptx::mbar_wait(&tempty[as], aphase ^ 1);  // epilogue(s) drained this accumulator
                     ptx::tc_fence_after();
                     const uint32_t d_tmem = tmem_base + as * kBN;
                     for (int kb = 0; kb < a.kb_count; ++kb) {
                         ptx::mbar_wait(&full[stage], phase);
                         ptx::tc_fence_after();
-                        const uint32_t sa = ptx::smem_u32(tiles + static_cast<size_t>(stage) * kStageBytes);
+                        const uint32_t sa = ptx::smem_u32(tiles + static_cast<size_t>(stage) * kStageBytesCta);
                         const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
                         const uint64_t db = ptx::make_kmajor_sw128_desc(sa + kABytes);
 #pragma unroll
                         for (int k = 0; k < kBK / kUmmaK; ++k) {
                             // advance 16 elements = 32 bytes along K inside the swizzle atom
                             const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
-                            ptx::umma_f16(d_tmem, da + koff, db + koff, idesc, (kb | k) != 0 ? 1u : 0u);
+                            if (CG == 2) ptx::umma_f16_pair(d_tmem, da + koff, db + koff, idesc, (kb | k) != 0 ? 1u : 0u);
+                            else ptx::umma_f16(d_tmem, da + koff, db + koff, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
-                        ptx::umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
-                        if (++stage == kStages) {
+                        // smem slot reusable (in both CTAs) once these MMAs retire
+                        if (CG == 2) ptx::umma_commit_pair(&empty[stage], 3);
+                        else ptx::umma_commit(&empty[stage]);
+                        if (++stage == kNumStages) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
-                    ptx::umma_commit(&tfull[as]);  // accumulator complete
+                    if (CG == 2) ptx::umma_commit_pair(&tfull[as], 3);  // accumulator complete (both CTAs)
+                    else ptx::umma_commit(&tfull[as]);
                 }
             }
         }
     } else {
-        // ================= epilogue: one thread = one query (TMEM lane) =================
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        // ================= epilogue: one thread = one query (TMEM lane) x half the columns =====
+        const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;     // which 128 of the tile's 256 columns
         const int lane_q = quad * 32 + lane;
+        const uint32_t lead_tempty0 = CG == 2 ? ptx::map_to_cta(ptx::smem_u32(&tempty[0]), 0) : 0;
         float tau[kMaxMT];
         float top[kMaxMT][kSampleTop];
 #pragma unroll
-        for (int m = 0; m < kMaxMT; ++m) {
+        for (int mb = 0; mb < kMaxMT; ++mb) {
+            const int m = CG == 2 ? static_cast<int>(cta_rank) : mb;
             const int q = m * kBM + lane_q;
-            tau[m] = INFINITY;
-            if (MODE == kMain && m < a.mt && q < a.nq) tau[m] = a.thr[q];
+            tau[mb] = INFINITY;
+            if (MODE == kMain && mb < n_mblocks && q < a.nq) tau[mb] = a.thr[q];
 #pragma unroll
-            for (int i = 0; i < kSampleTop; ++i) top[m][i] = -INFINITY;
+            for (int i = 0; i < kSampleTop; ++i) top[mb][i] = -INFINITY;
         }
         uint32_t item = 0;
-        for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
+        for (int w = unit; w < a.n_work; w += n_units) {
             const int64_t tile = (static_cast<int64_t>(w) * a.tile_mul) / a.tile_div;
-            const int64_t row0 = tile * kBN;
-            const int ncols = static_cast<int>(min(static_cast<int64_t>(kBN), a.n_rows - row0));
+            const int64_t row0 = tile * kBN + half * kEpiCols;
+            // columns of this warp's half that are real corpus rows (warp-uniform)
+            const int ncols = static_cast<int>(max(static_cast<int64_t>(0),
+                                                   min(static_cast<int64_t>(kEpiCols), a.n_rows - row0)));
 #pragma unroll
-            for (int m = 0; m < kMaxMT; ++m) {
-                if (m >= a.mt) break;
+            for (int mb = 0; mb < kMaxMT; ++mb) {
+                if (mb >= n_mblocks) break;
                 const uint32_t as = item & 1, aphase = (item >> 1) & 1;
                 ++item;
+                const int m = CG == 2 ? static_cast<int>(cta_rank) : mb;
                 const int q = m * kBM + lane_q;
-                const bool q_valid = q < a.nq;
                 ptx::mbar_wait(&tfull[as], aphase);
                 ptx::tc_fence_after();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * kBN;
-                for (int c0 = 0; c0 < ncols; c0 += 32) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32(taddr + c0, v);
-                    ptx::tmem_ld_wait();
-                    const int nvalid = min(32, ncols - c0);
+                const uint32_t taddr =
+                    tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * kBN + half * kEpiCols;
+
+                auto process = [&](const uint32_t (&v)[32], int c0) {
+                    const int nvalid = ncols - c0;  // >= 1 here; may exceed 32
                     if (MODE == kMain) {
-                        const float t = tau[m];
-                        const uint32_t rbase = static_cast<uint32_t>(row0 + c0);
+                        // branch-free screen: does any of the 32 dots reach the threshold?
+                        float mx = __uint_as_float(v[0]);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float x = __uint_as_float(v[i]);
-                            if (x >= t && i < nvalid) {
-                                const uint32_t slot = atomicAdd(&a.cand_count[q], 1u);
-                                if (slot < a.capg)
-                                    a.cand[static_cast<size_t>(q) * a.capg + slot] =
-                                        (static_cast<uint64_t>(v[i]) << 32) | (rbase + i);
+                        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                        const float t = tau[mb];
+                        if (mx >= t) {
+                            const uint32_t rbase = static_cast<uint32_t>(row0 + c0);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const float x = __uint_as_float(v[i]);
+                                if (x >= t && i < nvalid) {
+                                    const uint32_t slot = atomicAdd(&a.cand_count[q], 1u);
+                                    if (slot < a.capg)
+                                        a.cand[static_cast<size_t>(q) * a.capg + slot] =
+                                            (static_cast<uint64_t>(v[i]) << 32) | (rbase + i);
+                                }
                             }
                         }
                     } else if (MODE == kSample) {
+                        float mx = __uint_as_float(v[0]);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float x = __uint_as_float(v[i]);
-                            if (x > top[m][kSampleTop - 1] && i < nvalid) insert_top16(top[m], x);
+                        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                        if (mx > top[mb][kSampleTop - 1]) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const float x = __uint_as_float(v[i]);
+                                if (x > top[mb][kSampleTop - 1] && i < nvalid) insert_top16(top[mb], x);
+                            }
                         }
                     } else {
-                        if (q_valid) {
+                        if (q < a.nq) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i)
                                 if (i < nvalid)
                                     a.dump[static_cast<size_t>(q) * a.n_rows + row0 + c0 + i] = __uint_as_float(v[i]);
                         }
                     }
+                };
+
+                // two register buffers: the load of chunk c+1 is in flight while chunk c is screened
+                uint32_t va[32], vb[32];
+                if (ncols > 0) {
+                    ptx::tmem_ld_32x32(taddr, va);
+                    ptx::tmem_ld_wait();
+                }
+#pragma unroll
+                for (int c0 = 0; c0 < kEpiCols; c0 += 64) {
+                    if (c0 + 32 < ncols) ptx::tmem_ld_32x32(taddr + c0 + 32, vb);
+                    if (c0 < ncols) process(va, c0);
+                    ptx::tmem_ld_wait();
+                    if (c0 + 64 < ncols) ptx::tmem_ld_32x32(taddr + c0 + 64, va);
+                    if (c0 + 32 < ncols) process(vb, c0 + 32);
+                    ptx::tmem_ld_wait();
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+                if (lane == 0) {
+                    if (CG == 2) ptx::mbar_arrive_cluster(lead_tempty0 + as * 8);
+                    else ptx::mbar_arrive(&tempty[as]);
+                }
             }
         }
         if (MODE == kSample) {
 #pragma unroll
-            for (int m = 0; m < kMaxMT; ++m) {
-                if (m >= a.mt) break;
+            for (int mb = 0; mb < kMaxMT; ++mb) {
+                if (mb >= n_mblocks) break;
+                const int m = CG == 2 ? static_cast<int>(cta_rank) : mb;
                 const int q = m * kBM + lane_q;
-                float* dst = a.sample_top + (static_cast<size_t>(blockIdx.x) * kChunkQueries + q) * kSampleTop;
+                float* dst = a.sample_top + ((static_cast<size_t>(unit) * 2 + half) * kChunkQueries + q) * kSampleTop;
 #pragma unroll
-                for (int i = 0; i < kSampleTop; ++i) dst[i] = top[m][i];
+                for (int i = 0; i < kSampleTop; ++i) dst[i] = top[mb][i];
             }
         }
     }
 
+    // teardown: nobody may leave while the peer still reads its smem / signals its barriers
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CG == 2) ptx::cluster_sync_all();
+    else __syncthreads();
     if (warp == 1) {
         __syncwarp();
-        ptx::tmem_dealloc(tmem_base, kTmemCols);
+        if (CG == 2) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+        else ptx::tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -302,12 +376,12 @@ __global__ void query_prep_kernel(const float* q, T* out, int nq, int nq_pad, in
 
 // one CTA per query: 16th largest sampled dot -> admission threshold; resets the candidate counters
 __global__ void __launch_bounds__(256)
-threshold_kernel(const float* sample_top, int sample_ctas, int nq, float floor_score, int use_sample,
+threshold_kernel(const float* sample_top, int sample_units, int nq, float floor_score, int use_sample,
                  float* thr, float* floor_out, uint32_t* cand_count, int32_t* retry) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
     const int q = blockIdx.x, tid = threadIdx.x;
-    const int n = sample_ctas * kSampleTop;
+    const int n = sample_units * 2 * kSampleTop;  // two column halves per CTA / CTA pair
     int cap = 1;
     while (cap < n) cap <<= 1;
     if (cap < 2) cap = 2;
@@ -316,8 +390,8 @@ threshold_kernel(const float* sample_top, int sample_ctas, int nq, float floor_s
         for (int i = tid; i < cap; i += 256) {
             uint64_t key = 0;
             if (i < n) {
-                const int cta = i / kSampleTop, j = i % kSampleTop;
-                const float x = sample_top[(static_cast<size_t>(cta) * kChunkQueries + q) * kSampleTop + j];
+                const int list = i / kSampleTop, j = i % kSampleTop;
+                const float x = sample_top[(static_cast<size_t>(list) * kChunkQueries + q) * kSampleTop + j];
                 key = float_to_ord(x);
             }
             keys[i] = key;
@@ -470,7 +544,7 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
     p.off_q = off;
     off = align(off + static_cast<size_t>(p.nq_pad) * dim * 2);
     p.off_sample = off;
-    off = align(off + static_cast<size_t>(p.sample_ctas) * kChunkQueries * kSampleTop * sizeof(float));
+    off = align(off + static_cast<size_t>(p.sample_ctas) * 2 * kChunkQueries * kSampleTop * sizeof(float));
     p.off_thr = off;
     off = align(off + kChunkQueries * sizeof(float));
     p.off_floor = off;
@@ -483,15 +557,35 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
     return p;
 }
 
-template <int MODE>
-cudaError_t launch_kernel(const CUtensorMap& mq, const CUtensorMap& mc, const KernelArgs& ka, uint32_t idesc,
-                          int grid, cudaStream_t s) {
-    auto kern = mma_topk_kernel<MODE>;
+template <int MODE, int CG>
+cudaError_t launch_kernel_cg(const CUtensorMap& mq, const CUtensorMap& mc, const KernelArgs& ka, uint32_t idesc,
+                             int units, cudaStream_t s) {
+    auto kern = mma_topk_kernel<MODE, CG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(kSmemBytes));
     if (e != cudaSuccess) return e;
-    kern<<<grid, kMmaThreads, kSmemBytes, s>>>(mq, mc, ka, idesc);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(units * CG));
+    cfg.blockDim = dim3(kMmaThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, mq, mc, ka, idesc);
+}
+
+// mt == 2 (129..256 queries): CTA pairs; mt == 1: single CTAs
+template <int MODE>
+cudaError_t launch_kernel(const CUtensorMap& mq, const CUtensorMap& mc1, const CUtensorMap& mc2,
+                          const KernelArgs& ka, int dtype, int units, cudaStream_t s) {
+    const int fmt = dtype == TAV_BF16 ? 1 : 0;
+    if (ka.mt == 2) return launch_kernel_cg<MODE, 2>(mq, mc2, ka, ptx::make_idesc_f16(2 * kBM, kBN, fmt), units, s);
+    return launch_kernel_cg<MODE, 1>(mq, mc1, ka, ptx::make_idesc_f16(kBM, kBN, fmt), units, s);
 }
 
 cudaError_t prep_queries(const MmaArgs& a, void* dst, int nq_pad, cudaStream_t s) {
@@ -533,9 +627,9 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
     if (e != cudaSuccess) return e;
     ++n_launch;
 
-    CUtensorMap map_c;
-    if (!encode_map(&map_c, a.dtype, a.corpus, a.n_corpus, a.dim, kBN)) return cudaErrorUnknown;
-    const uint32_t idesc = ptx::make_idesc_f16(kBM, kBN, a.dtype == TAV_BF16 ? 1 : 0);
+    CUtensorMap map_c1, map_c2;  // corpus tile boxes: 256 rows (single CTA) / 128 rows (per CTA of a pair)
+    if (!encode_map(&map_c1, a.dtype, a.corpus, a.n_corpus, a.dim, kBN)) return cudaErrorUnknown;
+    if (!encode_map(&map_c2, a.dtype, a.corpus, a.n_corpus, a.dim, kBN / 2)) return cudaErrorUnknown;
 
     int ev_used = 0;
     for (int q0 = 0; q0 < a.nq; q0 += kChunkQueries) {
@@ -555,6 +649,9 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
         ka.cand = d_cand;
         ka.cand_count = d_count;
         ka.capg = p.capg;
+        const int max_units = mt == 2 ? std::max(1, p.sms / 2) : p.sms;
+        const int sample_units = std::max(1, std::min(p.n_sample, max_units));
+        const int main_units = std::min(p.n_tiles, max_units);
 
         const bool timed = a.ev && ev_used < a.ev_max;
         if (timed) {
@@ -565,14 +662,17 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
             ka.n_work = p.n_sample;
             ka.tile_mul = p.n_tiles;
             ka.tile_div = p.n_sample;
-            e = launch_kernel<kSample>(map_q, map_c, ka, idesc, p.sample_ctas, s);
+            e = launch_kernel<kSample>(map_q, map_c1, map_c2, ka, a.dtype, sample_units, s);
             if (e != cudaSuccess) return e;
             ++n_launch;
         }
         int cap = 2;
-        while (cap < p.sample_ctas * kSampleTop) cap <<= 1;
+        while (cap < sample_units * 2 * kSampleTop) cap <<= 1;
+        e = cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(static_cast<size_t>(cap) * sizeof(uint64_t)));
+        if (e != cudaSuccess) return e;
         threshold_kernel<<<nq, 256, static_cast<size_t>(cap) * sizeof(uint64_t), s>>>(
-            d_sample, p.sample_ctas, nq, a.floor_score, p.n_sample > 0 ? 1 : 0, d_thr, d_floor, d_count,
+            d_sample, sample_units, nq, a.floor_score, p.n_sample > 0 ? 1 : 0, d_thr, d_floor, d_count,
             a.retry_flags + q0);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         ++n_launch;
@@ -580,7 +680,7 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
         ka.n_work = p.n_tiles;
         ka.tile_mul = 1;
         ka.tile_div = 1;
-        e = launch_kernel<kMain>(map_q, map_c, ka, idesc, p.main_ctas, s);
+        e = launch_kernel<kMain>(map_q, map_c1, map_c2, ka, a.dtype, main_units, s);
         if (e != cudaSuccess) return e;
         ++n_launch;
         if (timed) {
@@ -613,9 +713,9 @@ cudaError_t launch_mma_dump(const MmaArgs& a, void* workspace, size_t workspace_
     void* d_q = ws + p.off_q;
     cudaError_t e = prep_queries(a, d_q, p.nq_pad, s);
     if (e != cudaSuccess) return e;
-    CUtensorMap map_c;
-    if (!encode_map(&map_c, a.dtype, a.corpus, a.n_corpus, a.dim, kBN)) return cudaErrorUnknown;
-    const uint32_t idesc = ptx::make_idesc_f16(kBM, kBN, a.dtype == TAV_BF16 ? 1 : 0);
+    CUtensorMap map_c1, map_c2;
+    if (!encode_map(&map_c1, a.dtype, a.corpus, a.n_corpus, a.dim, kBN)) return cudaErrorUnknown;
+    if (!encode_map(&map_c2, a.dtype, a.corpus, a.n_corpus, a.dim, kBN / 2)) return cudaErrorUnknown;
     for (int q0 = 0; q0 < a.nq; q0 += kChunkQueries) {
         const int nq = std::min(kChunkQueries, a.nq - q0);
         const int mt = (nq + kBM - 1) / kBM;
@@ -631,7 +731,8 @@ cudaError_t launch_mma_dump(const MmaArgs& a, void* workspace, size_t workspace_
         ka.tile_mul = 1;
         ka.tile_div = 1;
         ka.dump = out + static_cast<size_t>(q0) * a.n_corpus;
-        e = launch_kernel<kDump>(map_q, map_c, ka, idesc, p.main_ctas, s);
+        const int max_units = mt == 2 ? std::max(1, p.sms / 2) : p.sms;
+        e = launch_kernel<kDump>(map_q, map_c1, map_c2, ka, a.dtype, std::min(p.n_tiles, max_units), s);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
