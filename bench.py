@@ -321,9 +321,13 @@ def run_b200(args, w):
     if shard_bytes < 4e8:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
 
+    res_out = (torch.empty((batch, k), dtype=torch.int64, device=device),
+               torch.empty((batch, k), dtype=torch.float32, device=device),
+               torch.empty((batch,), dtype=torch.int32, device=device))
+
     def step_resident():
         if sharded is None:
-            return base.search_device(q_dev, k, w["min_score"])
+            return base.search_device(q_dev, k, w["min_score"], out=res_out)
         return sharded.search_tensors(q_dev, k, w["min_score"])
 
     def step_e2e():
@@ -401,13 +405,21 @@ def run_b200(args, w):
     clocks = sampler.stop() if sampler else None
 
     # roofline pass: the dominant kernel's own duration (events inside libtavec), per step
-    scan_ms = []
+    scan_ms, kinds_ms = [], {}
     for _ in range(args.steps):
         if flush is not None:
             flush.fill_(1)
         step_resident()
-        scan_ms.append(base.last_timing()["scan_ms"])
+        t = base.last_timing()
+        scan_ms.append(t["scan_ms"])
+        per_step = {}
+        for name, ms in t["kernels"]:
+            per_step[name] = per_step.get(name, 0.0) + ms
+        per_step["search_total"] = t["total_ms"]
+        for name, ms in per_step.items():
+            kinds_ms.setdefault(name, []).append(ms)
     kernel_ms = statistics.fmean(scan_ms)
+    breakdown = {name: statistics.fmean(v) for name, v in kinds_ms.items()}
 
     # sanity: the result of the last step is well-formed
     items, scores, counts = step_resident()
@@ -447,10 +459,11 @@ def run_b200(args, w):
             "bound": "hbm", "kernel": "scan_rows_kernel" if path == "scan" else "mma_topk_kernel",
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
             "of": peaks["source"], "traffic": None, "kernel_ms_per_step": kernel_ms,
+            "per_step_ms_by_kernel_kind": breakdown,
             "algorithmic_bytes_per_step": algo_bytes,
             "bytes_actually_requested_per_step": algo_launch_bytes,
             "note": "achieved = algorithmic bytes (corpus shard read once per batch) / event-timed duration of "
-                    "the dominant kernel(s) per step" + ("" if passes == 1 else
+                    "the dominant kernel (the MAIN launch of the tcgen05 kernel, or the row-scan kernel) per step" + ("" if passes == 1 else
                     f"; the row-scan path re-reads the corpus once per 8 queries ({passes} passes)"),
         },
         "clocks": clocks,

@@ -140,10 +140,15 @@ int tav_mma_scores(tav_index* ix, const float* queries, int n_queries, int flags
                    void* stream);
 
 /* Device time of the last tav_search on this index, measured with CUDA events on the
- * search's stream: `scan_ms` = the dominant kernel(s) (row scan or MMA kernel, summed over
- * query chunks), `total_ms` = first launch to last result byte on device; `launches` =
- * kernels launched; `path` = 1 row-scan kernels, 2 tcgen05 kernel.  Synchronises. */
+ * search's stream: `scan_ms` = the dominant kernel (row-scan kernel, or the MAIN launch of the
+ * tcgen05 kernel; summed over query chunks), `total_ms` = first launch to last result byte on
+ * device; `launches` = kernels launched; `path` = 1 row-scan kernels, 2 tcgen05 kernel.
+ * Synchronises. */
 int tav_last_timing(tav_index* ix, float* scan_ms, float* total_ms, int* launches, int* path);
+
+/* Per-kernel durations of the last tav_search, in launch order (up to `capacity` entries;
+ * *n = number recorded): kinds[i] = 0 dominant kernel, 1 sample pass, 2 auxiliary kernel. */
+int tav_timing_breakdown(tav_index* ix, float* ms, int* kinds, int capacity, int* n);
 
 #ifdef __cplusplus
 }

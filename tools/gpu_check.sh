@@ -29,11 +29,25 @@ for st in $stages; do
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
         --log-file gpurun_out/launches_c1.csv python bench.py --workload c1 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_c1.log 2>&1 ;;
     ncu_c3_list)
-      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv \
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"tav|mma_topk|threshold|finalize|query_prep|scan_rows|select|merge" -c 60 --csv \
         --log-file gpurun_out/launches_c3.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_c3_list.log 2>&1 ;;
     ncu_c3_full)
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:mma_topk -s 3 -c 1 \
         -o gpurun_out/prof_c3 -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_c3_full.log 2>&1 ;;
+    multi2)
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 \
+        tools/multi_gpu_check.py 2>&1 | tail -15 | tee gpurun_out/multi2.log ;;
+    bench_g2)
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 \
+        bench.py --gpus 2 --steps 40 --warmup 5 2>gpurun_out/bench_g2.err | tee gpurun_out/bench_g2.json ;;
+    multi8)
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 \
+        tools/multi_gpu_check.py 2>&1 | tail -15 | tee gpurun_out/multi8.log ;;
+    bench_g8)
+      for n in 2 4 8; do
+        timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2952$n \
+          bench.py --gpus $n --steps 40 --warmup 5 2>gpurun_out/bench_g$n.err | tee gpurun_out/bench_g$n.json
+      done ;;
     *) echo "unknown stage $st" ;;
   esac
 done

@@ -91,6 +91,7 @@ struct tav_index {
     // timing of the last search
     cudaEvent_t ev_total[2] = {nullptr, nullptr};
     cudaEvent_t ev_chunk[kMaxTimedChunks][2];
+    int ev_kind[kMaxTimedChunks];  // 0 dominant kernel, 1 sample pass, 2 auxiliary
     int timed_chunks = 0;
     int launches = 0;
     int path = 0;
@@ -385,7 +386,10 @@ static int scan_search(tav_index* ix, const float* d_queries, int nq_total, int 
             const bool timed = ix->timed_chunks < kMaxTimedChunks;
             if (timed) TAV_CUDA(cudaEventRecord(ix->ev_chunk[ix->timed_chunks][0], s));
             TAV_CUDA(launch_scan(a, s));
-            if (timed) TAV_CUDA(cudaEventRecord(ix->ev_chunk[ix->timed_chunks++][1], s));
+            if (timed) {
+                ix->ev_kind[ix->timed_chunks] = 0;
+                TAV_CUDA(cudaEventRecord(ix->ev_chunk[ix->timed_chunks++][1], s));
+            }
             SelectArgs sel{};
             sel.cand_keys = a.cand_keys;
             sel.cand_stride = cand_stride;
@@ -524,6 +528,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
         TAV_CUDA(ix->retry.ensure(static_cast<size_t>(n_queries) * sizeof(int32_t)));
         m.retry_flags = static_cast<int32_t*>(ix->retry.p);
         m.ev = ix->ev_chunk;
+        m.ev_kind = ix->ev_kind;
         m.ev_max = kMaxTimedChunks;
         int ev_used = 0;
         m.ev_used = &ev_used;
@@ -619,6 +624,24 @@ int tav_merge_topk(int device, int n_lists, int n_queries, int k, const int64_t*
     return TAV_OK;
 }
 
+int tav_timing_breakdown(tav_index* ix, float* ms, int* kinds, int capacity, int* n) {
+    if (!ix || !n || capacity < 0) return TAV_ERR_INVALID;
+    if (!ix->timing_valid) {
+        set_error("tav_timing_breakdown: no timed search on this index yet");
+        return TAV_ERR_STATE;
+    }
+    if (int rc = set_device(ix)) return rc;
+    TAV_CUDA(cudaEventSynchronize(ix->ev_total[1]));
+    *n = ix->timed_chunks;
+    for (int i = 0; i < ix->timed_chunks && i < capacity; ++i) {
+        float v = 0.0f;
+        TAV_CUDA(cudaEventElapsedTime(&v, ix->ev_chunk[i][0], ix->ev_chunk[i][1]));
+        if (ms) ms[i] = v;
+        if (kinds) kinds[i] = ix->ev_kind[i];
+    }
+    return TAV_OK;
+}
+
 int tav_last_timing(tav_index* ix, float* scan_ms, float* total_ms, int* launches, int* path) {
     if (!ix) return TAV_ERR_INVALID;
     if (!ix->timing_valid) {
@@ -630,6 +653,7 @@ int tav_last_timing(tav_index* ix, float* scan_ms, float* total_ms, int* launche
     float total = 0.0f, scan = 0.0f;
     TAV_CUDA(cudaEventElapsedTime(&total, ix->ev_total[0], ix->ev_total[1]));
     for (int i = 0; i < ix->timed_chunks; ++i) {
+        if (ix->ev_kind[i] != 0) continue;
         float ms = 0.0f;
         TAV_CUDA(cudaEventElapsedTime(&ms, ix->ev_chunk[i][0], ix->ev_chunk[i][1]));
         scan += ms;

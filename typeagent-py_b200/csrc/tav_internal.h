@@ -76,8 +76,9 @@ struct MmaArgs {
     float* out_scores;
     int32_t* out_counts;
     int32_t* retry_flags;  // device [nq]: set to 1 for queries the caller must redo with the row scan
-    cudaEvent_t (*ev)[2];  // optional event pairs, one recorded around each 256-query chunk's
-    int ev_max;            //   sample + threshold + main kernels
+    cudaEvent_t (*ev)[2];  // optional event pairs, one recorded around every kernel launched
+    int* ev_kind;          //   kind per pair: 0 = dominant (MAIN) kernel, 1 = sample pass, 2 = auxiliary
+    int ev_max;
     int* ev_used;
 };
 size_t mma_workspace_bytes(const MmaArgs& a);

@@ -653,17 +653,22 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
         const int sample_units = std::max(1, std::min(p.n_sample, max_units));
         const int main_units = std::min(p.n_tiles, max_units);
 
-        const bool timed = a.ev && ev_used < a.ev_max;
-        if (timed) {
-            e = cudaEventRecord(a.ev[ev_used][0], s);
-            if (e != cudaSuccess) return e;
-        }
+        auto ev_begin = [&]() -> cudaError_t {
+            return (a.ev && ev_used < a.ev_max) ? cudaEventRecord(a.ev[ev_used][0], s) : cudaSuccess;
+        };
+        auto ev_end = [&](int kind) -> cudaError_t {
+            if (!(a.ev && ev_used < a.ev_max)) return cudaSuccess;
+            if (a.ev_kind) a.ev_kind[ev_used] = kind;
+            return cudaEventRecord(a.ev[ev_used++][1], s);
+        };
         if (p.n_sample > 0) {
             ka.n_work = p.n_sample;
             ka.tile_mul = p.n_tiles;
             ka.tile_div = p.n_sample;
+            if ((e = ev_begin()) != cudaSuccess) return e;
             e = launch_kernel<kSample>(map_q, map_c1, map_c2, ka, a.dtype, sample_units, s);
             if (e != cudaSuccess) return e;
+            if ((e = ev_end(1)) != cudaSuccess) return e;
             ++n_launch;
         }
         int cap = 2;
@@ -671,32 +676,33 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
         e = cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(static_cast<size_t>(cap) * sizeof(uint64_t)));
         if (e != cudaSuccess) return e;
+        if ((e = ev_begin()) != cudaSuccess) return e;
         threshold_kernel<<<nq, 256, static_cast<size_t>(cap) * sizeof(uint64_t), s>>>(
             d_sample, sample_units, nq, a.floor_score, p.n_sample > 0 ? 1 : 0, d_thr, d_floor, d_count,
             a.retry_flags + q0);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = ev_end(2)) != cudaSuccess) return e;
         ++n_launch;
 
         ka.n_work = p.n_tiles;
         ka.tile_mul = 1;
         ka.tile_div = 1;
+        if ((e = ev_begin()) != cudaSuccess) return e;
         e = launch_kernel<kMain>(map_q, map_c1, map_c2, ka, a.dtype, main_units, s);
         if (e != cudaSuccess) return e;
+        if ((e = ev_end(0)) != cudaSuccess) return e;
         ++n_launch;
-        if (timed) {
-            e = cudaEventRecord(a.ev[ev_used][1], s);
-            if (e != cudaSuccess) return e;
-            ++ev_used;
-        }
 
         const size_t sel_smem = static_cast<size_t>(next_pow2(a.k + kSelectThreads)) * sizeof(uint64_t);
         e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(sel_smem));
         if (e != cudaSuccess) return e;
+        if ((e = ev_begin()) != cudaSuccess) return e;
         finalize_kernel<<<nq, kSelectThreads, sel_smem, s>>>(
             d_cand, d_count, p.capg, d_thr, d_floor, a.k, a.item_offset, a.out_items + static_cast<size_t>(q0) * a.k,
             a.out_scores + static_cast<size_t>(q0) * a.k, a.out_counts + q0, a.retry_flags + q0);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = ev_end(2)) != cudaSuccess) return e;
         ++n_launch;
     }
     if (launches) *launches = n_launch;

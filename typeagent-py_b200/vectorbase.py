@@ -382,8 +382,14 @@ class VectorBase:
         launches, path = C.c_int(0), C.c_int(0)
         _capi.check(lib.tav_last_timing(self._ix, C.byref(scan), C.byref(total), C.byref(launches),
                                         C.byref(path)))
+        ms = (C.c_float * 64)()
+        kinds = (C.c_int * 64)()
+        n = C.c_int(0)
+        _capi.check(lib.tav_timing_breakdown(self._ix, ms, kinds, 64, C.byref(n)))
+        names = {0: "main", 1: "sample", 2: "aux"}
+        breakdown = [(names.get(kinds[i], "?"), ms[i]) for i in range(min(n.value, 64))]
         return {"scan_ms": scan.value, "total_ms": total.value, "launches": launches.value,
-                "path": {1: "scan", 2: "mma"}.get(path.value, "none")}
+                "path": {1: "scan", 2: "mma"}.get(path.value, "none"), "kernels": breakdown}
 
     # ------------------------------------------------------------------ lookups
     @staticmethod
