@@ -62,7 +62,29 @@ struct DevBuf {
     }
 };
 
+// a grow-only pinned host buffer (staging for truly asynchronous H2D / D2H of small payloads)
+struct PinBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        size_t want = std::max(need, size_t(1) << 16);
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
 constexpr int kMaxTimedChunks = 64;
+constexpr size_t kPinnedStageLimit = size_t(8) << 20;  // payloads above this go straight from user memory
 
 }  // namespace tav
 
@@ -83,7 +105,11 @@ struct tav_index {
     DevBuf subset;      // int64 [subset_len]
     DevBuf cand_keys;   // [qb, cand_stride] uint64
     DevBuf cand_count;  // [qb] uint32 + [qb] uint64 bounds
-    DevBuf out_items, out_scores, out_counts;  // device result staging for host outputs
+    DevBuf out_pack;    // device result staging for host outputs: [items | scores | counts | retry]
+    PinBuf pin_in;      // pinned staging: queries (+ subset) on the way in
+    PinBuf pin_out;     // pinned staging: packed results on the way out
+    cudaEvent_t ev_pin_in = nullptr;  // completion of the last H2D that read pin_in
+    bool pin_in_busy = false;
     DevBuf staging;     // append: source rows before conversion
     DevBuf mma_ws;      // tensor-core path workspace
     DevBuf retry;       // int32 [n_queries]
@@ -97,6 +123,17 @@ struct tav_index {
     int path = 0;
     bool timing_valid = false;
 };
+
+// The pinned input staging may still be the source of an in-flight H2D copy when the previous
+// search returned without synchronising (device outputs): wait for that copy before reuse.
+static cudaError_t pin_in_acquire(tav_index* ix, size_t bytes) {
+    if (ix->pin_in_busy) {
+        cudaError_t e = cudaEventSynchronize(ix->ev_pin_in);
+        if (e != cudaSuccess) return e;
+        ix->pin_in_busy = false;
+    }
+    return ix->pin_in.ensure(bytes);
+}
 
 static int set_device(const tav_index* ix) {
     TAV_CUDA(cudaSetDevice(ix->device));
@@ -148,6 +185,7 @@ int tav_create(int device, int dim, int store_dtype, int index_flags, int64_t re
     ix->flags = index_flags;
     for (auto& pr : ix->ev_chunk) pr[0] = pr[1] = nullptr;
     cudaError_t ce = cudaEventCreate(&ix->ev_total[0]);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ix->ev_pin_in, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreate(&ix->ev_total[1]);
     for (int i = 0; ce == cudaSuccess && i < kMaxTimedChunks; ++i) {
         ce = cudaEventCreate(&ix->ev_chunk[i][0]);
@@ -175,11 +213,14 @@ int tav_destroy(tav_index* ix) {
     cudaSetDevice(ix->device);
     cudaDeviceSynchronize();  // searches may still be in flight on the caller's streams
     if (ix->rows && !ix->adopted) cudaFree(ix->rows);
-    for (DevBuf* b : {&ix->queries, &ix->subset, &ix->cand_keys, &ix->cand_count, &ix->out_items,
-                      &ix->out_scores, &ix->out_counts, &ix->staging, &ix->mma_ws, &ix->retry})
+    for (DevBuf* b : {&ix->queries, &ix->subset, &ix->cand_keys, &ix->cand_count, &ix->out_pack,
+                      &ix->staging, &ix->mma_ws, &ix->retry})
         b->release();
+    ix->pin_in.release();
+    ix->pin_out.release();
     for (auto& ev : ix->ev_total)
         if (ev) cudaEventDestroy(ev);
+    if (ix->ev_pin_in) cudaEventDestroy(ix->ev_pin_in);
     for (auto& pr : ix->ev_chunk)
         for (auto& ev : pr)
             if (ev) cudaEventDestroy(ev);
@@ -432,13 +473,17 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
     int64_t* d_items = out_items;
     float* d_scores = out_scores;
     int32_t* d_counts = out_counts;
+    // host outputs: results are packed [items | scores | counts] in one device buffer so that a
+    // single D2H copy (into pinned staging) brings them back
+    const size_t off_scores = nk * sizeof(int64_t);
+    const size_t off_counts = off_scores + ((nk * sizeof(float) + 7) & ~size_t(7));
+    const size_t pack_bytes = off_counts + ((static_cast<size_t>(n_queries) * sizeof(int32_t) + 7) & ~size_t(7));
     if (!o_dev) {
-        TAV_CUDA(ix->out_items.ensure(nk * sizeof(int64_t)));
-        TAV_CUDA(ix->out_scores.ensure(nk * sizeof(float)));
-        TAV_CUDA(ix->out_counts.ensure(static_cast<size_t>(n_queries) * sizeof(int32_t)));
-        d_items = static_cast<int64_t*>(ix->out_items.p);
-        d_scores = static_cast<float*>(ix->out_scores.p);
-        d_counts = static_cast<int32_t*>(ix->out_counts.p);
+        TAV_CUDA(ix->out_pack.ensure(pack_bytes));
+        char* base = static_cast<char*>(ix->out_pack.p);
+        d_items = reinterpret_cast<int64_t*>(base);
+        d_scores = reinterpret_cast<float*>(base + off_scores);
+        d_counts = reinterpret_cast<int32_t*>(base + off_counts);
     }
 
     const int64_t n_scan = subset ? subset_len : ix->size;
@@ -471,9 +516,16 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
                 return TAV_ERR_RANGE;
             }
         }
-        TAV_CUDA(ix->subset.ensure(static_cast<size_t>(subset_len) * sizeof(int64_t)));
-        TAV_CUDA(cudaMemcpyAsync(ix->subset.p, subset, static_cast<size_t>(subset_len) * sizeof(int64_t),
-                                 cudaMemcpyHostToDevice, s));
+        const size_t sub_bytes = static_cast<size_t>(subset_len) * sizeof(int64_t);
+        TAV_CUDA(ix->subset.ensure(sub_bytes));
+        const void* src = subset;
+        if (sub_bytes <= kPinnedStageLimit) {
+            TAV_CUDA(pin_in_acquire(ix, ((sub_bytes + 15) & ~size_t(15)) +
+                                            static_cast<size_t>(n_queries) * ix->dim * sizeof(float)));
+            memcpy(ix->pin_in.p, subset, sub_bytes);
+            src = ix->pin_in.p;
+        }
+        TAV_CUDA(cudaMemcpyAsync(ix->subset.p, src, sub_bytes, cudaMemcpyHostToDevice, s));
         d_subset = static_cast<const int64_t*>(ix->subset.p);
     }
 
@@ -494,9 +546,23 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
             TAV_CUDA(launch_convert(src, TAV_F32, ix->queries.p, TAV_F32, n_queries, ix->dim, 1, s));
             ix->launches += 1;
         } else {
-            TAV_CUDA(cudaMemcpyAsync(ix->queries.p, queries, q_bytes, cudaMemcpyHostToDevice, s));
+            const void* src = queries;
+            if (q_bytes <= kPinnedStageLimit) {
+                // via pinned staging: a pageable source would make the copy synchronous
+                const size_t sub_bytes = subset ? static_cast<size_t>(subset_len) * sizeof(int64_t) : 0;
+                const size_t sub_off = sub_bytes <= kPinnedStageLimit ? ((sub_bytes + 15) & ~size_t(15)) : 0;
+                TAV_CUDA(pin_in_acquire(ix, sub_off + q_bytes));
+                memcpy(static_cast<char*>(ix->pin_in.p) + sub_off, queries, q_bytes);
+                src = static_cast<char*>(ix->pin_in.p) + sub_off;
+            }
+            TAV_CUDA(cudaMemcpyAsync(ix->queries.p, src, q_bytes, cudaMemcpyHostToDevice, s));
         }
         d_queries = static_cast<const float*>(ix->queries.p);
+    }
+
+    if (o_dev && (!q_dev || subset)) {  // no synchronisation at the end of this call
+        TAV_CUDA(cudaEventRecord(ix->ev_pin_in, s));
+        ix->pin_in_busy = true;
     }
 
     // path choice: tensor cores for batches on 16-bit storage, row scan otherwise
@@ -561,11 +627,21 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
     ix->timing_valid = true;
 
     if (!o_dev) {
-        TAV_CUDA(cudaMemcpyAsync(out_items, d_items, nk * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-        TAV_CUDA(cudaMemcpyAsync(out_scores, d_scores, nk * sizeof(float), cudaMemcpyDeviceToHost, s));
-        TAV_CUDA(cudaMemcpyAsync(out_counts, d_counts, static_cast<size_t>(n_queries) * sizeof(int32_t),
-                                 cudaMemcpyDeviceToHost, s));
-        TAV_CUDA(cudaStreamSynchronize(s));
+        if (pack_bytes <= kPinnedStageLimit) {
+            TAV_CUDA(ix->pin_out.ensure(pack_bytes));
+            TAV_CUDA(cudaMemcpyAsync(ix->pin_out.p, ix->out_pack.p, pack_bytes, cudaMemcpyDeviceToHost, s));
+            TAV_CUDA(cudaStreamSynchronize(s));
+            const char* h = static_cast<const char*>(ix->pin_out.p);
+            memcpy(out_items, h, nk * sizeof(int64_t));
+            memcpy(out_scores, h + off_scores, nk * sizeof(float));
+            memcpy(out_counts, h + off_counts, static_cast<size_t>(n_queries) * sizeof(int32_t));
+        } else {
+            TAV_CUDA(cudaMemcpyAsync(out_items, d_items, nk * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            TAV_CUDA(cudaMemcpyAsync(out_scores, d_scores, nk * sizeof(float), cudaMemcpyDeviceToHost, s));
+            TAV_CUDA(cudaMemcpyAsync(out_counts, d_counts, static_cast<size_t>(n_queries) * sizeof(int32_t),
+                                     cudaMemcpyDeviceToHost, s));
+            TAV_CUDA(cudaStreamSynchronize(s));
+        }
     }
     return TAV_OK;
 }

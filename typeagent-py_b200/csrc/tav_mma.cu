@@ -60,7 +60,7 @@ constexpr int kMmaThreads = 64 + 32 * kEpiWarps;    // warp 0 TMA, warp 1 MMA, w
 constexpr int kEpiCols = kBN / 2;                   // columns per epilogue warp
 constexpr int kMaxMT = 2;                           // query blocks per launch (2 x 128 queries)
 constexpr int kChunkQueries = kBM * kMaxMT;         // 256
-constexpr int kSampleTop = 16;
+constexpr int kSampleTop = 8;                        // sampled dots kept per thread (see make_plan)
 constexpr int kTmemCols = 512;
 constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(kStages) * kStageBytes + 256;  // both forms: 192 KB of tiles
 
@@ -82,8 +82,8 @@ struct KernelArgs {
     float* dump;           // DUMP: [nq, n_rows] raw dots
 };
 
-__device__ __forceinline__ void insert_top16(float (&top)[kSampleTop], float x) {
-    // top[] sorted descending; x > top[15] on entry
+__device__ __forceinline__ void insert_top(float (&top)[kSampleTop], float x) {
+    // top[] sorted descending; x > top[last] on entry
 #pragma unroll
     for (int i = 0; i < kSampleTop; ++i) {
         const float hi = fmaxf(top[i], x);
@@ -278,7 +278,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
                             for (int i = 0; i < 32; ++i) {
                                 const float x = __uint_as_float(v[i]);
-                                if (x > top[mb][kSampleTop - 1] && i < nvalid) insert_top16(top[mb], x);
+                                if (x > top[mb][kSampleTop - 1] && i < nvalid) insert_top(top[mb], x);
                             }
                         }
                     } else {
@@ -374,35 +374,58 @@ __global__ void query_prep_kernel(const float* q, T* out, int nq, int nq_pad, in
     }
 }
 
-// one CTA per query: 16th largest sampled dot -> admission threshold; resets the candidate counters
+// One WARP per query: the kSampleTop-th largest sampled dot -> admission threshold; also resets
+// the candidate counters.  Every sampling thread left a descending list of its kSampleTop largest
+// dots; the global kSampleTop-th largest is found by popping the largest list head kSampleTop
+// times (warp arg-max over the lanes' lists) — a k-way merge that stops after kSampleTop items.
 __global__ void __launch_bounds__(256)
 threshold_kernel(const float* sample_top, int sample_units, int nq, float floor_score, int use_sample,
                  float* thr, float* floor_out, uint32_t* cand_count, int32_t* retry) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
-    const int q = blockIdx.x, tid = threadIdx.x;
-    const int n = sample_units * 2 * kSampleTop;  // two column halves per CTA / CTA pair
-    int cap = 1;
-    while (cap < n) cap <<= 1;
-    if (cap < 2) cap = 2;
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const int n_lists = sample_units * 2;  // two column halves per CTA / CTA pair
+    constexpr int kMaxListsPerLane = 10;   // 148 units x 2 halves / 32 lanes
     float result = -INFINITY;
     if (use_sample) {
-        for (int i = tid; i < cap; i += 256) {
-            uint64_t key = 0;
-            if (i < n) {
-                const int list = i / kSampleTop, j = i % kSampleTop;
-                const float x = sample_top[(static_cast<size_t>(list) * kChunkQueries + q) * kSampleTop + j];
-                key = float_to_ord(x);
+        int head[kMaxListsPerLane];
+#pragma unroll
+        for (int j = 0; j < kMaxListsPerLane; ++j) head[j] = 0;
+        for (int round = 0; round < kSampleTop; ++round) {
+            float best = -INFINITY;
+            int best_j = -1;
+#pragma unroll
+            for (int j = 0; j < kMaxListsPerLane; ++j) {
+                const int list = lane + 32 * j;
+                if (list < n_lists && head[j] < kSampleTop) {
+                    const float x = sample_top[(static_cast<size_t>(list) * kChunkQueries + q) * kSampleTop + head[j]];
+                    if (x > best) {
+                        best = x;
+                        best_j = j;
+                    }
+                }
             }
-            keys[i] = key;
+            float wbest = best;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) wbest = fmaxf(wbest, __shfl_xor_sync(0xFFFFFFFFu, wbest, off));
+            const unsigned owners = __ballot_sync(0xFFFFFFFFu, best == wbest && best_j >= 0);
+            if (owners == 0) {  // fewer than kSampleTop finite samples
+                wbest = -INFINITY;
+                result = wbest;
+                break;
+            }
+            if (lane == __ffs(owners) - 1) {
+#pragma unroll
+                for (int j = 0; j < kMaxListsPerLane; ++j)
+                    if (j == best_j) ++head[j];
+            }
+            result = wbest;
         }
-        bitonic_sort_desc<256>(keys, cap);
-        if (n >= kSampleTop) result = ord_to_float(static_cast<uint32_t>(keys[kSampleTop - 1]));
     }
-    if (tid == 0) {
+    if (lane == 0) {
         const float floor_x = dot_floor_for_score(floor_score);
         float t = floor_x;
-        if (use_sample && result > -INFINITY && !(result != result)) {
+        if (use_sample && result > -INFINITY) {
             // bottom of the float32 score class of the sampled dot: rows below it score strictly less
             const float snapped = dot_floor_for_score(score_from_dot(result));
             t = fmaxf(snapped, floor_x);
@@ -527,8 +550,14 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
     cudaDeviceGetAttribute(&p.sms, cudaDevAttrMultiProcessorCount, device);
     p.n_tiles = static_cast<int>((n_rows + kBN - 1) / kBN);
     p.kb_count = (dim + kBK - 1) / kBK;
-    const int64_t target = std::max<int64_t>(2048, 16ll * k);  // rows we aim to admit per query
-    if (n_rows <= 16384) {
+    // Rows we aim to admit per query.  The threshold is the m-th largest (m = kSampleTop) of a
+    // uniform sample of S = m*N/target rows, so about `target` rows of the corpus lie above it.
+    // Starvation (< k admitted) needs m of the corpus' top k inside the sample — expected k*m/target
+    // = 0.4 for k = 100: probability ~1e-9; overflow (> 8*target) is rarer still.  Either way the
+    // query is merely redone by the exact row scan.
+    // Small corpora aim lower (1/64 of the rows) so that the MAIN epilogue's slow path stays rare.
+    const int64_t target = std::max<int64_t>(16ll * k, std::min<int64_t>(2048, n_rows / 64));
+    if (n_rows <= 16384 || 8 * target >= n_rows) {
         p.n_sample = 0;
         p.capg = static_cast<uint32_t>(n_rows);
     } else {
@@ -650,7 +679,7 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
         ka.cand_count = d_count;
         ka.capg = p.capg;
         const int max_units = mt == 2 ? std::max(1, p.sms / 2) : p.sms;
-        const int sample_units = std::max(1, std::min(p.n_sample, max_units));
+        const int sample_units = std::max(1, std::min(std::min(p.n_sample, max_units), 160));  // <= 320 lists
         const int main_units = std::min(p.n_tiles, max_units);
 
         auto ev_begin = [&]() -> cudaError_t {
@@ -671,15 +700,10 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
             if ((e = ev_end(1)) != cudaSuccess) return e;
             ++n_launch;
         }
-        int cap = 2;
-        while (cap < sample_units * 2 * kSampleTop) cap <<= 1;
-        e = cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(static_cast<size_t>(cap) * sizeof(uint64_t)));
-        if (e != cudaSuccess) return e;
         if ((e = ev_begin()) != cudaSuccess) return e;
-        threshold_kernel<<<nq, 256, static_cast<size_t>(cap) * sizeof(uint64_t), s>>>(
-            d_sample, sample_units, nq, a.floor_score, p.n_sample > 0 ? 1 : 0, d_thr, d_floor, d_count,
-            a.retry_flags + q0);
+        threshold_kernel<<<(nq + 7) / 8, 256, 0, s>>>(d_sample, sample_units, nq, a.floor_score,
+                                                      p.n_sample > 0 ? 1 : 0, d_thr, d_floor, d_count,
+                                                      a.retry_flags + q0);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if ((e = ev_end(2)) != cudaSuccess) return e;
         ++n_launch;
