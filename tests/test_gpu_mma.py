@@ -76,6 +76,33 @@ def test_search_matches_oracle(storage, n, d, b, k, ms):
         assert_hits_match(batch[i], O.lookup(vr, qr[i], k, ms), min_score=ms, what=f"{storage} q{i}")
 
 
+@pytest.mark.parametrize("storage,n,d,b,k,ms", [
+    ("bfloat16", 50000, 384, 1000, 5, 0.0),     # BASELINE configs[4] shape
+    ("bfloat16", 50000, 384, 40, 5, 0.56),      # threshold cuts most rows
+    ("float16", 300, 64, 130, 8, 0.0),          # corpus smaller than one tile... and k = register limit
+    ("bfloat16", 70000, 128, 256, 1, 0.0),
+    ("float16", 20000, 200, 17, 3, 0.9),        # nothing passes for most queries
+])
+def test_in_register_topk_small_k(storage, n, d, b, k, ms):
+    """k <= 8 takes the in-register top-k epilogue (no sampling, no candidate buffers)."""
+    v, q = O.make_corpus(n, d, seed=n + b + k, n_queries=b)
+    vr, qr = O.round_to_storage(v, storage), O.round_to_storage(q, storage)
+    base = make_base(v, storage)
+    batch = base.fuzzy_lookup_embeddings(qr, max_hits=k, min_score=ms)
+    t = base.last_timing()
+    assert t["path"] == "mma" and not any(name == "sample" for name, _ in t["kernels"])
+    for i in list(range(min(b, 10))) + [b // 2, b - 1]:
+        assert_hits_match(batch[i], O.lookup(vr, qr[i], k, ms), min_score=ms, what=f"{storage} q{i}")
+
+
+def test_in_register_topk_ties_and_duplicates():
+    row = O.round_to_bfloat16(O.make_corpus(1, 64, seed=9)[0])
+    same = np.repeat(row, 20000, axis=0)
+    base = make_base(same, "bfloat16")
+    for hits in base.fuzzy_lookup_embeddings(np.repeat(row, 20, axis=0), 7, 0.0):
+        assert [h.item for h in hits] == list(range(19999, 19992, -1))
+
+
 def test_unrounded_float32_queries_are_rounded_like_the_corpus():
     v, q = O.make_corpus(20000, 256, seed=5, n_queries=20)
     base = make_base(v, "bfloat16")

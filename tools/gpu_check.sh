@@ -48,6 +48,12 @@ for st in $stages; do
         timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2952$n \
           bench.py --gpus $n --steps 40 --warmup 5 2>gpurun_out/bench_g$n.err | tee gpurun_out/bench_g$n.json
       done ;;
+    ncu_c5_full)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:mma_topk -s 4 -c 1 \
+        -o gpurun_out/prof_c5 -f python bench.py --workload c5 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_c5_full.log 2>&1 ;;
+    ncu_c5_list)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"tav|mma_topk|threshold|finalize|query_prep|scan_rows|select|merge" -c 60 --csv \
+        --log-file gpurun_out/launches_c5.csv python bench.py --workload c5 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_c5_list.log 2>&1 ;;
     *) echo "unknown stage $st" ;;
   esac
 done

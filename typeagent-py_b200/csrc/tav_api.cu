@@ -398,16 +398,19 @@ static int scan_search(tav_index* ix, const float* d_queries, int nq_total, int 
     const int grid = scan_grid(ix->device, ix->dtype, ix->dim, qb, pass_k, n_scan);
     const int cand_stride = grid * pass_k;
     TAV_CUDA(ix->cand_keys.ensure(static_cast<size_t>(qb) * cand_stride * sizeof(uint64_t)));
-    TAV_CUDA(ix->cand_count.ensure(static_cast<size_t>(qb) * (sizeof(uint32_t) + sizeof(uint64_t)) + 64));
+    if (ix->cand_count.bytes < 8 * (sizeof(uint32_t) + sizeof(uint64_t)) + 64) {
+        // sized for the largest pass (8 queries) once, zeroed once; select_kernel re-zeroes the counters
+        TAV_CUDA(ix->cand_count.ensure(8 * (sizeof(uint32_t) + sizeof(uint64_t)) + 64));
+        TAV_CUDA(cudaMemsetAsync(ix->cand_count.p, 0, ix->cand_count.bytes, s));
+    }
     uint64_t* d_bound = static_cast<uint64_t*>(ix->cand_count.p);
-    uint32_t* d_count = reinterpret_cast<uint32_t*>(d_bound + qb);
+    uint32_t* d_count = reinterpret_cast<uint32_t*>(d_bound + 8);
     const int n_pass = (k + pass_k - 1) / pass_k;
 
     for (int q0 = 0; q0 < nq_total; q0 += qb) {
         const int nq = std::min(qb, nq_total - q0);
         for (int pass = 0; pass < n_pass; ++pass) {
             const int kk = std::min(pass_k, k - pass * pass_k);
-            TAV_CUDA(cudaMemsetAsync(d_count, 0, static_cast<size_t>(qb) * sizeof(uint32_t), s));
             ScanArgs a{};
             a.corpus = ix->rows;
             a.dtype = ix->dtype;
@@ -435,6 +438,7 @@ static int scan_search(tav_index* ix, const float* d_queries, int nq_total, int 
             sel.cand_keys = a.cand_keys;
             sel.cand_stride = cand_stride;
             sel.cand_count = d_count;
+            sel.cand_count_reset = d_count;
             sel.nq = nq;
             sel.k = kk;
             sel.out_stride = k;

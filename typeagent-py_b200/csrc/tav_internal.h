@@ -23,7 +23,7 @@ struct ScanArgs {
     int k;                    // hits kept per query this pass (<= kPassK)
     uint64_t* cand_keys;      // [nq, cand_stride] per-query global candidate buffers
     int cand_stride;
-    uint32_t* cand_count;     // [nq], zeroed by the caller
+    uint32_t* cand_count;     // [nq], zero on entry (the select kernel re-zeroes it)
     int grid;                 // CTAs to launch (cand_stride >= grid * k)
 };
 int scan_max_queries(int dim, int k);            // how many queries one pass can take (smem)
@@ -34,6 +34,7 @@ struct SelectArgs {
     const uint64_t* cand_keys;   // [nq, cand_stride]
     int cand_stride;
     const uint32_t* cand_count;  // [nq]
+    uint32_t* cand_count_reset;  // same array: zeroed by the kernel once consumed
     int nq;
     int k;                       // hits this pass
     int out_stride;              // row stride of out_items/out_scores (the caller's total k)

@@ -64,7 +64,8 @@ constexpr int kSampleTop = 8;                        // sampled dots kept per th
 constexpr int kTmemCols = 512;
 constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(kStages) * kStageBytes + 256;  // both forms: 192 KB of tiles
 
-enum Mode { kSample = 0, kMain = 1, kDump = 2 };
+enum Mode { kSample = 0, kMain = 1, kDump = 2, kRegTop = 3 };
+constexpr int kRegK = 8;  // REGTOP mode: hits kept per thread in registers (serves k <= 8)
 
 struct KernelArgs {
     int64_t n_rows;
@@ -80,6 +81,8 @@ struct KernelArgs {
     uint32_t* cand_count;  // MAIN: [256]
     uint32_t capg;
     float* dump;           // DUMP: [nq, n_rows] raw dots
+    uint64_t* reg_top;     // REGTOP: [units, 2 column halves, 256, kRegK] keys + 1 (0 = empty), descending
+    float floor_score;     // REGTOP: (float)min_score
 };
 
 __device__ __forceinline__ void insert_top(float (&top)[kSampleTop], float x) {
@@ -98,6 +101,16 @@ __device__ __forceinline__ void insert_top(float (&top)[kSampleTop], float x) {
 //         M=256 x N=256 across the pair, so each CTA's shared memory sees half of the operand
 //         traffic of the single-CTA form — the single-CTA form is smem-bandwidth bound at ~55 %
 //         of the tensor pipe (profiles/README.md).
+__device__ __forceinline__ void insert_key(uint64_t (&top)[kRegK], uint64_t key) {
+    // top[] sorted descending; key > top[last] on entry
+#pragma unroll
+    for (int i = 0; i < kRegK; ++i) {
+        const uint64_t hi = top[i] > key ? top[i] : key;
+        key = top[i] > key ? key : top[i];
+        top[i] = hi;
+    }
+}
+
 template <int MODE, int CG>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
@@ -221,6 +234,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t lead_tempty0 = CG == 2 ? ptx::map_to_cta(ptx::smem_u32(&tempty[0]), 0) : 0;
         float tau[kMaxMT];
         float top[kMaxMT][kSampleTop];
+        uint64_t rk[kMaxMT][kRegK];  // REGTOP: best keys (+1) of this thread's columns, descending
 #pragma unroll
         for (int mb = 0; mb < kMaxMT; ++mb) {
             const int m = CG == 2 ? static_cast<int>(cta_rank) : mb;
@@ -229,6 +243,8 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             if (MODE == kMain && mb < n_mblocks && q < a.nq) tau[mb] = a.thr[q];
 #pragma unroll
             for (int i = 0; i < kSampleTop; ++i) top[mb][i] = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < kRegK; ++i) rk[mb][i] = 0;
         }
         uint32_t item = 0;
         for (int w = unit; w < a.n_work; w += n_units) {
@@ -281,6 +297,22 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                                 if (x > top[mb][kSampleTop - 1] && i < nvalid) insert_top(top[mb], x);
                             }
                         }
+                    } else if (MODE == kRegTop) {
+                        // in-register top-k: screen the chunk's best score against the thread's worst kept key
+                        float mx = __uint_as_float(v[0]);
+#pragma unroll
+                        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                        const float smx = score_from_dot(mx);
+                        if (smx >= a.floor_score && make_key(smx, 0xFFFFFFFFu) >= rk[mb][kRegK - 1]) {
+                            const uint32_t rbase = static_cast<uint32_t>(row0 + c0);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const float sc = score_from_dot(__uint_as_float(v[i]));
+                                const uint64_t key1 = make_key(sc, rbase + i) + 1;
+                                if (sc >= a.floor_score && i < nvalid && key1 > rk[mb][kRegK - 1])
+                                    insert_key(rk[mb], key1);
+                            }
+                        }
                     } else {
                         if (q < a.nq) {
 #pragma unroll
@@ -323,6 +355,17 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 float* dst = a.sample_top + ((static_cast<size_t>(unit) * 2 + half) * kChunkQueries + q) * kSampleTop;
 #pragma unroll
                 for (int i = 0; i < kSampleTop; ++i) dst[i] = top[mb][i];
+            }
+        }
+        if (MODE == kRegTop) {
+#pragma unroll
+            for (int mb = 0; mb < kMaxMT; ++mb) {
+                if (mb >= n_mblocks) break;
+                const int m = CG == 2 ? static_cast<int>(cta_rank) : mb;
+                const int q = m * kBM + lane_q;
+                uint64_t* dst = a.reg_top + ((static_cast<size_t>(unit) * 2 + half) * kChunkQueries + q) * kRegK;
+#pragma unroll
+                for (int i = 0; i < kRegK; ++i) dst[i] = rk[mb][i];
             }
         }
     }
@@ -437,6 +480,63 @@ threshold_kernel(const float* sample_top, int sample_units, int nq, float floor_
     }
 }
 
+// REGTOP merge — one WARP per query: k-way merge of the per-thread descending key lists, stopping
+// after k items; writes the final hits.
+__global__ void __launch_bounds__(256)
+regtop_merge_kernel(const uint64_t* reg_top, int units, int nq, int k, int64_t item_offset, int64_t* out_items,
+                    float* out_scores, int32_t* out_counts, int32_t* retry) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const int n_lists = units * 2;
+    constexpr int kMaxListsPerLane = 10;
+    int head[kMaxListsPerLane];
+#pragma unroll
+    for (int j = 0; j < kMaxListsPerLane; ++j) head[j] = 0;
+    int n_out = 0;
+    for (int round = 0; round < k; ++round) {
+        uint64_t best = 0;
+        int best_j = -1;
+#pragma unroll
+        for (int j = 0; j < kMaxListsPerLane; ++j) {
+            const int list = lane + 32 * j;
+            if (list < n_lists && head[j] < kRegK) {
+                const uint64_t key1 = reg_top[(static_cast<size_t>(list) * kChunkQueries + q) * kRegK + head[j]];
+                if (key1 > best) {
+                    best = key1;
+                    best_j = j;
+                }
+            }
+        }
+        uint64_t wbest = best;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, wbest, off);
+            wbest = o > wbest ? o : wbest;
+        }
+        if (wbest == 0) break;  // every list exhausted (keys are stored +1; 0 = empty)
+        if (best == wbest) {    // keys are unique: exactly one lane owns it
+#pragma unroll
+            for (int j = 0; j < kMaxListsPerLane; ++j)
+                if (j == best_j) ++head[j];
+        }
+        if (lane == 0) {
+            const uint64_t key = wbest - 1;
+            out_items[static_cast<size_t>(q) * k + n_out] = static_cast<int64_t>(key_pos(key)) + item_offset;
+            out_scores[static_cast<size_t>(q) * k + n_out] = key_score(key);
+        }
+        ++n_out;
+    }
+    if (lane == 0) {
+        for (int j = n_out; j < k; ++j) {
+            out_items[static_cast<size_t>(q) * k + j] = -1;
+            out_scores[static_cast<size_t>(q) * k + j] = 0.0f;
+        }
+        out_counts[q] = n_out;
+        retry[q] = 0;
+    }
+}
+
 // one CTA per query: admitted (dot,row) pairs -> scores -> top-k, or flag the query for the row scan
 __global__ void __launch_bounds__(kSelectThreads)
 finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t capg, const float* thr,
@@ -542,6 +642,7 @@ struct Plan {
     int nq_pad;        // all queries, padded to 128
     // workspace offsets
     size_t off_q, off_sample, off_thr, off_floor, off_count, off_cand, total;
+    bool reg_top;      // k <= kRegK: in-register top-k, no sampling / candidate buffers
 };
 
 Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
@@ -550,6 +651,7 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
     cudaDeviceGetAttribute(&p.sms, cudaDevAttrMultiProcessorCount, device);
     p.n_tiles = static_cast<int>((n_rows + kBN - 1) / kBN);
     p.kb_count = (dim + kBK - 1) / kBK;
+    p.reg_top = k <= kRegK;
     // Rows we aim to admit per query.  The threshold is the m-th largest (m = kSampleTop) of a
     // uniform sample of S = m*N/target rows, so about `target` rows of the corpus lie above it.
     // Starvation (< k admitted) needs m of the corpus' top k inside the sample — expected k*m/target
@@ -572,8 +674,9 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
     size_t off = 0;
     p.off_q = off;
     off = align(off + static_cast<size_t>(p.nq_pad) * dim * 2);
-    p.off_sample = off;
-    off = align(off + static_cast<size_t>(p.sample_ctas) * 2 * kChunkQueries * kSampleTop * sizeof(float));
+    p.off_sample = off;  // SAMPLE lists (float x kSampleTop) or REGTOP lists (u64 x kRegK), per unit and half
+    off = align(off + static_cast<size_t>(std::max(p.sample_ctas, p.reg_top ? p.main_ctas : 0)) * 2 * kChunkQueries *
+                          std::max(kSampleTop * sizeof(float), kRegK * sizeof(uint64_t)));
     p.off_thr = off;
     off = align(off + kChunkQueries * sizeof(float));
     p.off_floor = off;
@@ -581,7 +684,7 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
     p.off_count = off;
     off = align(off + kChunkQueries * sizeof(uint32_t));
     p.off_cand = off;
-    off = align(off + static_cast<size_t>(kChunkQueries) * p.capg * sizeof(uint64_t));
+    off = align(off + (p.reg_top ? 0 : static_cast<size_t>(kChunkQueries) * p.capg * sizeof(uint64_t)));
     p.total = off;
     return p;
 }
@@ -690,6 +793,28 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
             if (a.ev_kind) a.ev_kind[ev_used] = kind;
             return cudaEventRecord(a.ev[ev_used++][1], s);
         };
+        if (p.reg_top) {
+            // k <= 8: top-k kept in registers across the whole corpus, then a warp-per-query merge
+            ka.n_work = p.n_tiles;
+            ka.tile_mul = 1;
+            ka.tile_div = 1;
+            ka.reg_top = reinterpret_cast<uint64_t*>(d_sample);
+            ka.floor_score = a.floor_score;
+            if ((e = ev_begin()) != cudaSuccess) return e;
+            e = launch_kernel<kRegTop>(map_q, map_c1, map_c2, ka, a.dtype, std::min(main_units, 160), s);
+            if (e != cudaSuccess) return e;
+            if ((e = ev_end(0)) != cudaSuccess) return e;
+            ++n_launch;
+            if ((e = ev_begin()) != cudaSuccess) return e;
+            regtop_merge_kernel<<<(nq + 7) / 8, 256, 0, s>>>(
+                ka.reg_top, std::min(main_units, 160), nq, a.k, a.item_offset,
+                a.out_items + static_cast<size_t>(q0) * a.k, a.out_scores + static_cast<size_t>(q0) * a.k,
+                a.out_counts + q0, a.retry_flags + q0);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if ((e = ev_end(2)) != cudaSuccess) return e;
+            ++n_launch;
+            continue;
+        }
         if (p.n_sample > 0) {
             ka.n_work = p.n_sample;
             ka.tile_mul = p.n_tiles;

@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(const SelectArgs
     if (tid == 0) {
         a.out_counts[q] = a.accumulate ? a.out_counts[q] + n : n;
         if (a.bound_out) a.bound_out[q] = (n == a.k) ? keys[a.k - 1] : 0;
+        a.cand_count_reset[q] = 0;  // ready for the next pass: no memset between launches
     }
 }
 
