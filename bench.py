@@ -306,6 +306,8 @@ def run_b200(args, w):
         base = sharded._engine.base
         base.force_path = force
 
+    base.enable_timing()  # events around the kernels: needed for the roofline block
+
     rng = np.random.default_rng(7)
     q_host = torch.empty((batch, dim), dtype=torch.float32).pin_memory()
     qn = rng.standard_normal((batch, dim)).astype(np.float32)

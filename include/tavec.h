@@ -139,11 +139,15 @@ int tav_merge_topk(int device, int n_lists, int n_queries, int k, const int64_t*
 int tav_mma_scores(tav_index* ix, const float* queries, int n_queries, int flags, float* out_device,
                    void* stream);
 
+/* Event timing is off by default (four fewer driver calls per search); enable it before the
+ * searches you want timed.  Path and launch count are always recorded. */
+int tav_set_timing(tav_index* ix, int enabled);
+
 /* Device time of the last tav_search on this index, measured with CUDA events on the
  * search's stream: `scan_ms` = the dominant kernel (row-scan kernel, or the MAIN launch of the
  * tcgen05 kernel; summed over query chunks), `total_ms` = first launch to last result byte on
- * device; `launches` = kernels launched; `path` = 1 row-scan kernels, 2 tcgen05 kernel.
- * Synchronises. */
+ * device (both -1 when timing is off); `launches` = kernels launched; `path` = 1 row-scan
+ * kernels, 2 tcgen05 kernel.  Synchronises when timing is on. */
 int tav_last_timing(tav_index* ix, float* scan_ms, float* total_ms, int* launches, int* path);
 
 /* Per-kernel durations of the last tav_search, in launch order (up to `capacity` entries;

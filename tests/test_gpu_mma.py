@@ -29,6 +29,7 @@ def make_base(v, storage, path="mma"):
     base = tab.VectorBase(tab.TextEmbeddingIndexSettings(O.FakeEmbeddingModel()), storage_dtype=storage)
     base.add_embeddings(None, v)
     base.force_path = path
+    base.enable_timing()
     return base
 
 

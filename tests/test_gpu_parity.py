@@ -339,6 +339,7 @@ def test_device_tensor_handles_and_timing():
     v, q = O.make_corpus(9000, 128, 141, n_queries=6)
     t = torch.from_numpy(v).cuda()
     base = tab.VectorBase.from_device_tensor(tab.TextEmbeddingIndexSettings(O.FakeEmbeddingModel()), t)
+    base.enable_timing()
     assert len(base) == 9000
     items, scores, counts = base.search_device(torch.from_numpy(q).cuda(), 12, 0.0)
     torch.cuda.synchronize()

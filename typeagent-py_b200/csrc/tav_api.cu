@@ -122,6 +122,7 @@ struct tav_index {
     int launches = 0;
     int path = 0;
     bool timing_valid = false;
+    bool timing_on = false;  // record CUDA events around kernels (tav_set_timing)
 };
 
 // The pinned input staging may still be the source of an in-flight H2D copy when the previous
@@ -427,7 +428,7 @@ static int scan_search(tav_index* ix, const float* d_queries, int nq_total, int 
             a.cand_stride = cand_stride;
             a.cand_count = d_count;
             a.grid = grid;
-            const bool timed = ix->timed_chunks < kMaxTimedChunks;
+            const bool timed = ix->timing_on && ix->timed_chunks < kMaxTimedChunks;
             if (timed) TAV_CUDA(cudaEventRecord(ix->ev_chunk[ix->timed_chunks][0], s));
             TAV_CUDA(launch_scan(a, s));
             if (timed) {
@@ -533,7 +534,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
         d_subset = static_cast<const int64_t*>(ix->subset.p);
     }
 
-    TAV_CUDA(cudaEventRecord(ix->ev_total[0], s));
+    if (ix->timing_on) TAV_CUDA(cudaEventRecord(ix->ev_total[0], s));
 
     // queries -> device float32 (normalised in place when the index is TAV_NORMALIZE)
     const float* d_queries = queries;
@@ -597,7 +598,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
         m.out_counts = d_counts;
         TAV_CUDA(ix->retry.ensure(static_cast<size_t>(n_queries) * sizeof(int32_t)));
         m.retry_flags = static_cast<int32_t*>(ix->retry.p);
-        m.ev = ix->ev_chunk;
+        m.ev = ix->timing_on ? ix->ev_chunk : nullptr;
         m.ev_kind = ix->ev_kind;
         m.ev_max = kMaxTimedChunks;
         int ev_used = 0;
@@ -627,7 +628,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
                              d_items, d_scores, d_counts, nullptr, s);
         if (rc != TAV_OK) return rc;
     }
-    TAV_CUDA(cudaEventRecord(ix->ev_total[1], s));
+    if (ix->timing_on) TAV_CUDA(cudaEventRecord(ix->ev_total[1], s));
     ix->timing_valid = true;
 
     if (!o_dev) {
@@ -704,11 +705,18 @@ int tav_merge_topk(int device, int n_lists, int n_queries, int k, const int64_t*
     return TAV_OK;
 }
 
+int tav_set_timing(tav_index* ix, int enabled) {
+    if (!ix) return TAV_ERR_INVALID;
+    ix->timing_on = enabled != 0;
+    ix->timing_valid = false;
+    return TAV_OK;
+}
+
 int tav_timing_breakdown(tav_index* ix, float* ms, int* kinds, int capacity, int* n) {
     if (!ix || !n || capacity < 0) return TAV_ERR_INVALID;
-    if (!ix->timing_valid) {
-        set_error("tav_timing_breakdown: no timed search on this index yet");
-        return TAV_ERR_STATE;
+    if (!ix->timing_valid || !ix->timing_on) {
+        *n = 0;
+        return TAV_OK;
     }
     if (int rc = set_device(ix)) return rc;
     TAV_CUDA(cudaEventSynchronize(ix->ev_total[1]));
@@ -727,6 +735,13 @@ int tav_last_timing(tav_index* ix, float* scan_ms, float* total_ms, int* launche
     if (!ix->timing_valid) {
         set_error("tav_last_timing: no timed search on this index yet");
         return TAV_ERR_STATE;
+    }
+    if (!ix->timing_on) {  // path / launch count only
+        if (scan_ms) *scan_ms = -1.0f;
+        if (total_ms) *total_ms = -1.0f;
+        if (launches) *launches = ix->launches;
+        if (path) *path = ix->path;
+        return TAV_OK;
     }
     if (int rc = set_device(ix)) return rc;
     TAV_CUDA(cudaEventSynchronize(ix->ev_total[1]));

@@ -62,7 +62,9 @@ constexpr int kMaxMT = 2;                           // query blocks per launch (
 constexpr int kChunkQueries = kBM * kMaxMT;         // 256
 constexpr int kSampleTop = 8;                        // sampled dots kept per thread (see make_plan)
 constexpr int kTmemCols = 512;
-constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(kStages) * kStageBytes + 256;  // both forms: 192 KB of tiles
+// both forms: 192 KB of tiles + barriers + a 32 KB epilogue scratch (one 32-float column per thread)
+constexpr size_t kScratchBytes = static_cast<size_t>(kEpiWarps) * 32 * 32 * sizeof(float);
+constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(kStages) * kStageBytes + 256 + kScratchBytes;
 
 enum Mode { kSample = 0, kMain = 1, kDump = 2, kRegTop = 3 };
 constexpr int kRegK = 8;  // REGTOP mode: hits kept per thread in registers (serves k <= 8)
@@ -127,6 +129,11 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     uint64_t* tfull = bars + 2 * kNumStages;  // [2] MMA -> epilogue      (each CTA its own)
     uint64_t* tempty = tfull + 2;             // [2] epilogue -> MMA      (the leader's copy is used)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    // epilogue scratch [32][kEpiWarps*32]: the insertion-heavy slow paths (SAMPLE, REGTOP) walk a
+    // chunk's 32 values in a ROLLED loop (registers cannot be indexed dynamically; unrolling 32
+    // insertion networks x 8 chunk sites blew the instruction cache: 38 % of epilogue cycles were
+    // instruction-fetch stalls, profiles/README.md).  MAIN's slow path is light and stays unrolled.
+    float* scratch_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0;
@@ -265,16 +272,31 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const uint32_t taddr =
                     tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * kBN + half * kEpiCols;
 
-                auto process = [&](const uint32_t (&v)[32], int c0) {
-                    const int nvalid = ncols - c0;  // >= 1 here; may exceed 32
-                    if (MODE == kMain) {
-                        // branch-free screen: does any of the 32 dots reach the threshold?
-                        float mx = __uint_as_float(v[0]);
+                float* scratch = scratch_all + (threadIdx.x - 64);  // element i at scratch[i * 256]
+                auto spill = [&](const uint32_t (&v)[32]) {
 #pragma unroll
-                        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; ++i) scratch[i * (kEpiWarps * 32)] = __uint_as_float(v[i]);
+                };
+                auto process = [&](const uint32_t (&v)[32], int c0) {
+                    const int nvalid = min(32, ncols - c0);  // >= 1 here
+                    if (MODE == kDump) {
+                        if (q < a.nq) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i < nvalid)
+                                    a.dump[static_cast<size_t>(q) * a.n_rows + row0 + c0 + i] = __uint_as_float(v[i]);
+                        }
+                        return;
+                    }
+                    // branch-free screen: the chunk's best dot
+                    float mx = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    const uint32_t rbase = static_cast<uint32_t>(row0 + c0);
+                    if (MODE == kMain) {
+                        // admitted rows are rare (one compare + predicated branch each): stays in registers
                         const float t = tau[mb];
                         if (mx >= t) {
-                            const uint32_t rbase = static_cast<uint32_t>(row0 + c0);
 #pragma unroll
                             for (int i = 0; i < 32; ++i) {
                                 const float x = __uint_as_float(v[i]);
@@ -287,38 +309,24 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                             }
                         }
                     } else if (MODE == kSample) {
-                        float mx = __uint_as_float(v[0]);
-#pragma unroll
-                        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
                         if (mx > top[mb][kSampleTop - 1]) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float x = __uint_as_float(v[i]);
-                                if (x > top[mb][kSampleTop - 1] && i < nvalid) insert_top(top[mb], x);
+                            spill(v);
+#pragma unroll 1
+                            for (int i = 0; i < nvalid; ++i) {
+                                const float x = scratch[i * (kEpiWarps * 32)];
+                                if (x > top[mb][kSampleTop - 1]) insert_top(top[mb], x);
                             }
                         }
-                    } else if (MODE == kRegTop) {
-                        // in-register top-k: screen the chunk's best score against the thread's worst kept key
-                        float mx = __uint_as_float(v[0]);
-#pragma unroll
-                        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    } else {  // kRegTop: in-register top-k
                         const float smx = score_from_dot(mx);
                         if (smx >= a.floor_score && make_key(smx, 0xFFFFFFFFu) >= rk[mb][kRegK - 1]) {
-                            const uint32_t rbase = static_cast<uint32_t>(row0 + c0);
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float sc = score_from_dot(__uint_as_float(v[i]));
+                            spill(v);
+#pragma unroll 1
+                            for (int i = 0; i < nvalid; ++i) {
+                                const float sc = score_from_dot(scratch[i * (kEpiWarps * 32)]);
                                 const uint64_t key1 = make_key(sc, rbase + i) + 1;
-                                if (sc >= a.floor_score && i < nvalid && key1 > rk[mb][kRegK - 1])
-                                    insert_key(rk[mb], key1);
+                                if (sc >= a.floor_score && key1 > rk[mb][kRegK - 1]) insert_key(rk[mb], key1);
                             }
-                        }
-                    } else {
-                        if (q < a.nq) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (i < nvalid)
-                                    a.dump[static_cast<size_t>(q) * a.n_rows + row0 + c0 + i] = __uint_as_float(v[i]);
                         }
                     }
                 };
@@ -329,7 +337,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     ptx::tmem_ld_32x32(taddr, va);
                     ptx::tmem_ld_wait();
                 }
-#pragma unroll
+#pragma unroll 1
                 for (int c0 = 0; c0 < kEpiCols; c0 += 64) {
                     if (c0 + 32 < ncols) ptx::tmem_ld_32x32(taddr + c0 + 32, vb);
                     if (c0 < ncols) process(va, c0);

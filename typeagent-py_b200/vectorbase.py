@@ -123,6 +123,7 @@ class VectorBase:
         self._device_only_rows = 0  # rows living only on the device (from_device_tensor)
         self._adopted_tensor = None
         self.force_path: str | None = None  # "scan" | "mma" | None (tests / benchmarks)
+        self._timing = False
         self.clear()
 
     # ------------------------------------------------------------------ housekeeping
@@ -288,6 +289,8 @@ class VectorBase:
             self._ix = handle
             self._ix_generation = -1
             self._ix_rows = 0
+            if self._timing:
+                _capi.check(lib.tav_set_timing(self._ix, 1))
         if self._device_only_rows:
             return lib, self._ix
         if self._ix_generation != self._generation:
@@ -375,8 +378,15 @@ class VectorBase:
         )
         return items, scores, counts
 
+    def enable_timing(self, enabled: bool = True) -> None:
+        """Record CUDA events around the kernels of subsequent lookups (see ``last_timing``)."""
+        self._timing = bool(enabled)
+        if self._ix is not None:
+            _capi.check(_capi.load().tav_set_timing(self._ix, 1 if enabled else 0))
+
     def last_timing(self) -> dict:
-        """Device time of the last lookup (CUDA events inside libtavec)."""
+        """Path, launch count and — after ``enable_timing()`` — device times of the last lookup
+        (CUDA events inside libtavec; ``scan_ms`` / ``total_ms`` are -1 when timing is off)."""
         lib = _capi.load()
         scan, total = C.c_float(0), C.c_float(0)
         launches, path = C.c_int(0), C.c_int(0)
