@@ -153,7 +153,7 @@ def run_reference_impl(args, w):
         "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_RESULT_OUT, flush=True)
 
 
 def workload_config(args, w, n_gpus):
@@ -328,9 +328,15 @@ def run_b200(args, w):
                torch.empty((batch,), dtype=torch.int32, device=device))
 
     def step_resident():
+        # fully asynchronous; the "did any query need the exact fallback" check of every step is
+        # accumulated on the device and resolved by finish_resident() inside the timed region
         if sharded is None:
-            return base.search_device(q_dev, k, w["min_score"], out=res_out)
-        return sharded.search_tensors(q_dev, k, w["min_score"])
+            return base.search_device(q_dev, k, w["min_score"], out=res_out, defer_check=True)
+        return sharded.search_tensors(q_dev, k, w["min_score"], defer_check=True)
+
+    def finish_resident():
+        redone = base.finish_search() if sharded is None else sharded.finish()
+        assert redone == 0, f"{redone} queries took the exact fallback on synthetic data"
 
     def step_e2e():
         # public host API: pinned host queries -> H2D -> search -> D2H of the hits
@@ -359,6 +365,7 @@ def run_b200(args, w):
             e0.record()
             for _ in range(steps):
                 fn()
+            finish_resident()
             e1.record()
             barrier()
             return e0.elapsed_time(e1)
@@ -369,6 +376,7 @@ def run_b200(args, w):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
+            finish_resident()
             e1.record()
             barrier()
             total += e0.elapsed_time(e1)
@@ -384,6 +392,7 @@ def run_b200(args, w):
     # warm-up (both legs), then the timed regions
     for _ in range(args.warmup):
         step_resident()
+        finish_resident()
         step_e2e()
     barrier()
 
@@ -415,6 +424,7 @@ def run_b200(args, w):
         if flush is not None:
             flush.fill_(1)
         step_resident()
+        finish_resident()
         t = base.last_timing()
         scan_ms.append(t["scan_ms"])
         per_step = {}
@@ -428,6 +438,7 @@ def run_b200(args, w):
 
     # sanity: the result of the last step is well-formed
     items, scores, counts = step_resident()
+    finish_resident()
     torch.cuda.synchronize()
     assert int(counts.min()) == min(k, rows) and bool((scores[:, :-1] >= scores[:, 1:]).all())
     assert int(items.min()) >= 0 and int(items.max()) < rows
@@ -481,9 +492,12 @@ def run_b200(args, w):
         cb = cpu_reference_leg(w, args.cpu_sample_rows, args.cpu_sample_queries)
         out["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
         out["cpu_baseline"]["sample_gbs"] = cb["sample_gbs"]
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+_RESULT_OUT = sys.stdout
 
 
 class _NullModel:
@@ -494,6 +508,11 @@ class _NullModel:
 
 
 def main():
+    # Libraries (NCCL prints "NCCL version ..." to stdout) must not pollute the one-JSON-line
+    # contract: route fd 1 to stderr for the whole run and keep a private handle for the result.
+    global _RESULT_OUT
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse_args()
     w = dict(WORKLOADS[args.workload])
     for name in ("rows", "batch", "k"):

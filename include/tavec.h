@@ -62,7 +62,11 @@ enum tav_search_flags {
     TAV_QUERIES_ON_DEVICE = 1, /* `queries` is a device pointer (float32 [n_queries, dim]) */
     TAV_OUTPUTS_ON_DEVICE = 2, /* out_* are device pointers; no synchronisation */
     TAV_FORCE_SCAN = 4,        /* use the CUDA-core row-scan kernels whatever the shape */
-    TAV_FORCE_MMA = 8          /* use the tcgen05 tensor-core kernel (bf16/fp16 storage only) */
+    TAV_FORCE_MMA = 8,         /* use the tcgen05 tensor-core kernel (bf16/fp16 storage only) */
+    /* Fully asynchronous tensor-core search (needs both ..._ON_DEVICE flags): the check whether
+     * some query must be redone by the exact row scan — a host synchronisation — is left to
+     * tav_finish_search.  Until then the outputs of such (rare) queries are not final. */
+    TAV_DEFER_RETRY = 16
 };
 
 int tav_abi_version(void);
@@ -115,6 +119,15 @@ int tav_read_rows(tav_index* ix, int64_t first, int64_t n, float* out_host, void
 int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float min_score,
                int flags, const int64_t* subset, int64_t subset_len, int64_t item_offset,
                int64_t* out_items, float* out_scores, int32_t* out_counts, void* stream);
+
+/* Completes a TAV_DEFER_RETRY search: synchronises `stream`, redoes flagged queries exactly into
+ * the same outputs and reports how many (*redone).  The arguments repeat the deferred call.
+ * Several deferred searches may precede one finish; if an EARLIER one needed the fallback the
+ * call fails with TAV_ERR_STATE (its outputs were never corrected).  No-op when nothing is
+ * pending. */
+int tav_finish_search(tav_index* ix, const float* queries_device, int n_queries, int k, float min_score,
+                      int64_t item_offset, int64_t* out_items, float* out_scores, int32_t* out_counts,
+                      void* stream, int* redone);
 
 /*
  * Merge step of the row-sharded search: `n_lists` per-shard results of

@@ -159,3 +159,33 @@ def test_fallback_when_the_sampled_threshold_cannot_decide():
     got = base.fuzzy_lookup_embeddings(qr, 400, 0.0)
     for hits, qq in zip(got, qr):
         assert_hits_match(hits, O.lookup(vr, qq, 400, 0.0))
+
+
+def test_deferred_check_async_search_and_finish():
+    """search_device(defer_check=True) never synchronises; finish_search() redoes flagged queries."""
+    import torch
+
+    # (a) ordinary data: nothing to redo, results final right after the stream drains
+    v, q = O.make_corpus(30000, 128, seed=12, n_queries=40)
+    vr, qr = O.round_to_bfloat16(v), O.round_to_bfloat16(q)
+    base = make_base(v, "bfloat16")
+    qd = torch.from_numpy(qr).cuda()
+    items, scores, counts = base.search_device(qd, 20, 0.0, defer_check=True)
+    assert base.finish_search() == 0 and base.finish_search() == 0
+    for b in range(0, 40, 7):
+        got = {"items": items[b, : counts[b]].tolist(), "scores": scores[b, : counts[b]].tolist()}
+        assert_hits_match(got, O.lookup(vr, qr[b], 20, 0.0))
+    # (b) every score ties -> candidate overflow -> every query flagged -> exact after finish
+    row = O.round_to_bfloat16(O.make_corpus(1, 64, seed=9)[0])
+    same = make_base(np.repeat(row, 30000, axis=0), "bfloat16")
+    qd = torch.from_numpy(np.repeat(row, 5, axis=0)).cuda()
+    items, scores, counts = same.search_device(qd, 9, 0.0, defer_check=True)
+    assert same.finish_search() == 5
+    torch.cuda.synchronize()
+    for b in range(5):
+        assert items[b].tolist() == list(range(29999, 29990, -1)) and int(counts[b]) == 9
+    # an unfinished flagged search is reported by the next finish
+    same.search_device(qd, 9, 0.0, defer_check=True)
+    same.search_device(qd, 9, 0.0, defer_check=True)
+    with pytest.raises(RuntimeError, match="never finished"):
+        same.finish_search()

@@ -59,6 +59,17 @@ def main():
         if rank == 0:
             print(f"multi-gpu ok: world={world} {storage} n={n} d={d} b={b} k={k} path={whole.last_timing()['path']}",
                   flush=True)
+    # pathological scores (all rows identical): every rank's tensor-core search flags its queries,
+    # finish() redoes them exactly and repeats the exchange
+    row = O.round_to_bfloat16(O.make_corpus(1, 64, seed=9)[0])
+    same = np.repeat(row, 20000 * world, axis=0)
+    sh = ShardedVectorBase(settings, device=local, storage_dtype="bfloat16")
+    sh.deserialize(same)
+    items, scores, counts = sh.search_arrays(np.repeat(row, 3, axis=0), 6, 0.0)
+    n = len(same)
+    assert items.tolist() == [list(range(n - 1, n - 7, -1))] * 3, items
+    if rank == 0:
+        print(f"multi-gpu ok: world={world} exact fallback through finish()", flush=True)
     dist.destroy_process_group()
 
 

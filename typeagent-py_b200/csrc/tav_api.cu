@@ -112,7 +112,9 @@ struct tav_index {
     bool pin_in_busy = false;
     DevBuf staging;     // append: source rows before conversion
     DevBuf mma_ws;      // tensor-core path workspace
-    DevBuf retry;       // int32 [n_queries]
+    DevBuf retry;       // int32 [n_queries] flags of the last tensor-core search + [1] running total at the end
+    int retry_capacity = 0;      // queries the flag array is sized for
+    int pending_queries = 0;     // > 0: a TAV_DEFER_RETRY search awaits tav_finish_search
 
     // timing of the last search
     cudaEvent_t ev_total[2] = {nullptr, nullptr};
@@ -458,6 +460,57 @@ static int scan_search(tav_index* ix, const float* d_queries, int nq_total, int 
     return TAV_OK;
 }
 
+}  // extern "C"
+
+// Synchronising tail of a tensor-core search: read the retry flags, redo flagged queries exactly.
+static int resolve_retries(tav_index* ix, const float* d_queries, int n_queries, int k, float min_score,
+                           int64_t item_offset, int64_t* d_items, float* d_scores, int32_t* d_counts,
+                           cudaStream_t s, int* redone) {
+    std::vector<int32_t> host(static_cast<size_t>(n_queries) + 1);
+    int32_t* flags = static_cast<int32_t*>(ix->retry.p);
+    TAV_CUDA(cudaMemcpyAsync(host.data(), flags, static_cast<size_t>(n_queries) * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, s));
+    TAV_CUDA(cudaMemcpyAsync(&host[n_queries], flags + ix->retry_capacity, sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, s));
+    TAV_CUDA(cudaStreamSynchronize(s));
+    ix->pending_queries = 0;
+    const int total = host[n_queries];
+    int n_flagged = 0;
+    for (int q = 0; q < n_queries; ++q) {
+        if (!host[q]) continue;
+        ++n_flagged;
+        int rc = scan_search(ix, d_queries + static_cast<size_t>(q) * ix->dim, 1, k, min_score, nullptr,
+                             ix->size, item_offset, d_items + static_cast<size_t>(q) * k,
+                             d_scores + static_cast<size_t>(q) * k, d_counts + q, nullptr, s);
+        if (rc != TAV_OK) return rc;
+    }
+    if (total != 0) TAV_CUDA(cudaMemsetAsync(flags + ix->retry_capacity, 0, sizeof(int32_t), s));
+    if (redone) *redone = n_flagged;
+    if (total != n_flagged) {
+        set_error("%d queries of earlier deferred searches needed the exact fallback but were never finished",
+                  total - n_flagged);
+        return TAV_ERR_STATE;
+    }
+    return TAV_OK;
+}
+
+extern "C" {
+
+int tav_finish_search(tav_index* ix, const float* queries_device, int n_queries, int k, float min_score,
+                      int64_t item_offset, int64_t* out_items, float* out_scores, int32_t* out_counts,
+                      void* stream, int* redone) {
+    if (!ix || n_queries < 0) return TAV_ERR_INVALID;
+    if (redone) *redone = 0;
+    if (ix->pending_queries == 0) return TAV_OK;  // nothing deferred (row-scan path, or already finished)
+    if (n_queries != ix->pending_queries || !queries_device || !out_items || !out_scores || !out_counts || k < 1) {
+        set_error("tav_finish_search: arguments must repeat the deferred tav_search call");
+        return TAV_ERR_INVALID;
+    }
+    if (int rc = set_device(ix)) return rc;
+    return resolve_retries(ix, queries_device, n_queries, k, min_score, item_offset, out_items, out_scores,
+                           out_counts, static_cast<cudaStream_t>(stream), redone);
+}
+
 int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float min_score,
                int flags, const int64_t* subset, int64_t subset_len, int64_t item_offset,
                int64_t* out_items, float* out_scores, int32_t* out_counts, void* stream) {
@@ -596,8 +649,20 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
         m.out_items = d_items;
         m.out_scores = d_scores;
         m.out_counts = d_counts;
-        TAV_CUDA(ix->retry.ensure(static_cast<size_t>(n_queries) * sizeof(int32_t)));
+        if (n_queries > ix->retry_capacity) {
+            // [flags x capacity | total]; the running total lives right after the flags
+            int32_t carried = 0;
+            if (ix->retry.p)
+                TAV_CUDA(cudaMemcpy(&carried, static_cast<int32_t*>(ix->retry.p) + ix->retry_capacity,
+                                    sizeof(int32_t), cudaMemcpyDeviceToHost));
+            const int cap = std::max(n_queries, 1024);
+            TAV_CUDA(ix->retry.ensure((static_cast<size_t>(cap) + 1) * sizeof(int32_t)));
+            TAV_CUDA(cudaMemcpy(static_cast<int32_t*>(ix->retry.p) + cap, &carried, sizeof(int32_t),
+                                cudaMemcpyHostToDevice));
+            ix->retry_capacity = cap;
+        }
         m.retry_flags = static_cast<int32_t*>(ix->retry.p);
+        m.retry_total = m.retry_flags + ix->retry_capacity;
         m.ev = ix->timing_on ? ix->ev_chunk : nullptr;
         m.ev_kind = ix->ev_kind;
         m.ev_max = kMaxTimedChunks;
@@ -610,16 +675,14 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
         ix->timed_chunks = ev_used;
         ix->launches += launches;
         // Queries the sampled admission threshold could not settle (fewer than k admitted rows
-        // although rows were cut, or candidate overflow) are redone exactly by the row scan.
-        std::vector<int32_t> retry(n_queries);
-        TAV_CUDA(cudaMemcpyAsync(retry.data(), m.retry_flags, retry.size() * sizeof(int32_t),
-                                 cudaMemcpyDeviceToHost, s));
-        TAV_CUDA(cudaStreamSynchronize(s));
-        for (int q = 0; q < n_queries; ++q) {
-            if (!retry[q]) continue;
-            int rc = scan_search(ix, d_queries + static_cast<size_t>(q) * ix->dim, 1, k, min_score,
-                                 nullptr, n_scan, item_offset, d_items + static_cast<size_t>(q) * k,
-                                 d_scores + static_cast<size_t>(q) * k, d_counts + q, nullptr, s);
+        // although rows were cut, or candidate overflow) are redone exactly by the row scan —
+        // now, or in tav_finish_search when the caller defers the (synchronising) check.
+        if ((flags & TAV_DEFER_RETRY) && o_dev && q_dev) {
+            ix->pending_queries = n_queries;
+        } else {
+            int redone = 0;
+            int rc = resolve_retries(ix, d_queries, n_queries, k, min_score, item_offset, d_items, d_scores,
+                                     d_counts, s, &redone);
             if (rc != TAV_OK) return rc;
         }
     } else {

@@ -77,6 +77,7 @@ struct MmaArgs {
     float* out_scores;
     int32_t* out_counts;
     int32_t* retry_flags;  // device [nq]: set to 1 for queries the caller must redo with the row scan
+    int32_t* retry_total;  // device [1]: incremented once per flagged query (never reset by the kernels)
     cudaEvent_t (*ev)[2];  // optional event pairs, one recorded around every kernel launched
     int* ev_kind;          //   kind per pair: 0 = dominant (MAIN) kernel, 1 = sample pass, 2 = auxiliary
     int ev_max;

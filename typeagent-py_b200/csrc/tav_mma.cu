@@ -549,7 +549,7 @@ regtop_merge_kernel(const uint64_t* reg_top, int units, int nq, int k, int64_t i
 __global__ void __launch_bounds__(kSelectThreads)
 finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t capg, const float* thr,
                 const float* floor_x, int k, int64_t item_offset, int64_t* out_items, float* out_scores,
-                int32_t* out_counts, int32_t* retry) {
+                int32_t* out_counts, int32_t* retry, int32_t* retry_total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
     __shared__ int s_cnt;
@@ -569,6 +569,7 @@ finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t capg,
         if (tid == 0) {
             out_counts[q] = 0;
             retry[q] = 1;
+            atomicAdd(retry_total, 1);
         }
         return;
     }
@@ -857,7 +858,7 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
         if ((e = ev_begin()) != cudaSuccess) return e;
         finalize_kernel<<<nq, kSelectThreads, sel_smem, s>>>(
             d_cand, d_count, p.capg, d_thr, d_floor, a.k, a.item_offset, a.out_items + static_cast<size_t>(q0) * a.k,
-            a.out_scores + static_cast<size_t>(q0) * a.k, a.out_counts + q0, a.retry_flags + q0);
+            a.out_scores + static_cast<size_t>(q0) * a.k, a.out_counts + q0, a.retry_flags + q0, a.retry_total);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if ((e = ev_end(2)) != cudaSuccess) return e;
         ++n_launch;

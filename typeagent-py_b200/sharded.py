@@ -67,7 +67,10 @@ class CudaShardEngine:
     def append_rows(self, rows: np.ndarray) -> None:
         self.base.add_embeddings(None, rows)
 
-    def search_packed(self, queries, k: int, min_score: float, item_offset: int):
+    def finish(self) -> int:
+        return self.base.finish_search()
+
+    def search_packed(self, queries, k: int, min_score: float, item_offset: int, defer_check: bool = False):
         torch = self.torch
         if isinstance(queries, np.ndarray):
             queries = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).to(
@@ -82,7 +85,7 @@ class CudaShardEngine:
             counts.zero_()
         else:
             self.base.search_device(queries, k, min_score, item_offset=item_offset,
-                                    out=(items, scores, counts))
+                                    out=(items, scores, counts), defer_check=defer_check)
         return buf
 
     def merge(self, gathered, world: int, n_queries: int, k: int):
@@ -187,22 +190,57 @@ class ShardedVectorBase:
                 self.settings.embedding_model.add_embedding(key, row)
 
     # ---- lookups -----------------------------------------------------------------------
-    def search_tensors(self, queries, k: int, min_score: float = 0.0):
-        """SPMD lookup; returns engine tensors (items, scores, counts), replicated on every
-        rank.  ``queries``: float32 [B, D] numpy array or engine-device tensor."""
+    def _gather_and_merge(self, local, b: int, k: int):
         import torch
 
-        n = len(self)
-        b = int(queries.shape[0])
-        k = max(1, min(int(k), max(n, 1)))
-        lo, _ = self.local_range
-        local = self._engine.search_packed(queries, k, float(np.float32(min_score)), lo)
         if self.world == 1:
             gathered = local.view(1, -1)
         else:
             gathered = torch.empty((self.world, local.numel()), dtype=torch.uint8, device=local.device)
             self._dist.all_gather_into_tensor(gathered.view(-1), local, group=self._group)
         return self._engine.merge(gathered, self.world, b, k)
+
+    def search_tensors(self, queries, k: int, min_score: float = 0.0, defer_check: bool = False):
+        """SPMD lookup; returns engine tensors (items, scores, counts), replicated on every
+        rank.  ``queries``: float32 [B, D] numpy array or engine-device tensor.
+
+        The local search, the candidate all-gather and the merge are enqueued back to back
+        without a host synchronisation; the (rare) "redo this query exactly" check runs at the
+        end — immediately, or in ``finish()`` when ``defer_check`` is set — and repeats the
+        exchange only if some rank actually had to redo a query."""
+        n = len(self)
+        b = int(queries.shape[0])
+        k = max(1, min(int(k), max(n, 1)))
+        lo, _ = self.local_range
+        deferrable = hasattr(self._engine, "finish")
+        local = (self._engine.search_packed(queries, k, float(np.float32(min_score)), lo, defer_check=True)
+                 if deferrable else self._engine.search_packed(queries, k, float(np.float32(min_score)), lo))
+        out = self._gather_and_merge(local, b, k)
+        self._pending = (local, b, k, out) if deferrable else None
+        if not defer_check:
+            self.finish()
+        return out
+
+    def finish(self) -> int:
+        """Resolve a deferred lookup on every rank; returns the number of queries (summed over
+        ranks) that took the exact fallback.  Collective: every rank must call it."""
+        import torch
+
+        pending = getattr(self, "_pending", None)
+        if pending is None:
+            return 0
+        local, b, k, out = pending
+        self._pending = None
+        redone = self._engine.finish()
+        total = redone
+        if self.world > 1:
+            t = torch.tensor([redone], dtype=torch.int32, device=local.device)
+            self._dist.all_reduce(t, group=self._group)
+            total = int(t.item())
+        if total > 0:  # some shard corrected its candidates: exchange and merge again, in place
+            items, scores, counts = self._gather_and_merge(local, b, k)
+            out[0].copy_(items), out[1].copy_(scores), out[2].copy_(counts)
+        return total
 
     def search_arrays(self, queries: np.ndarray, k: int, min_score: float = 0.0):
         q = np.ascontiguousarray(queries, dtype=np.float32)

@@ -540,10 +540,13 @@ class VectorBase:
         self._device_only_rows = tensor.shape[0]
         return self
 
-    def search_device(self, queries, k: int, min_score: float = 0.0, item_offset: int = 0, out=None):
-        """Lookup with torch CUDA tensors as handles, enqueued on torch's current stream and
-        not synchronised: queries float32 [B, D] -> (items int64 [B,k], scores float32 [B,k],
-        counts int32 [B]) on the device."""
+    def search_device(self, queries, k: int, min_score: float = 0.0, item_offset: int = 0, out=None,
+                      defer_check: bool = False):
+        """Lookup with torch CUDA tensors as handles, enqueued on torch's current stream:
+        queries float32 [B, D] -> (items int64 [B,k], scores float32 [B,k], counts int32 [B]) on
+        the device.  The tensor-core path normally ends with one host synchronisation (did any
+        query need the exact fallback?); with ``defer_check=True`` the call is fully
+        asynchronous and ``finish_search()`` must run before the results are trusted."""
         import torch
 
         if not (queries.is_cuda and queries.dtype == torch.float32 and queries.is_contiguous()):
@@ -562,10 +565,32 @@ class VectorBase:
         items, scores, counts = out
         stream = torch.cuda.current_stream(queries.device).cuda_stream
         flags = _capi.TAV_QUERIES_ON_DEVICE | _capi.TAV_OUTPUTS_ON_DEVICE | self._flags()
+        if defer_check:
+            flags |= _capi.TAV_DEFER_RETRY
+        floor = float(np.float32(min_score))
         _capi.check(
-            lib.tav_search(ix, C.c_void_p(queries.data_ptr()), b, k, C.c_float(float(np.float32(min_score))),
+            lib.tav_search(ix, C.c_void_p(queries.data_ptr()), b, k, C.c_float(floor),
                            flags, None, 0, item_offset, C.c_void_p(items.data_ptr()),
                            C.c_void_p(scores.data_ptr()), C.c_void_p(counts.data_ptr()),
                            C.c_void_p(stream))
         )
+        # arguments (and tensors, kept alive) a deferred call must repeat in finish_search()
+        self._pending = (queries, b, k, floor, item_offset, items, scores, counts, stream) if defer_check else None
         return items, scores, counts
+
+    def finish_search(self) -> int:
+        """Complete a ``search_device(..., defer_check=True)``: synchronise, redo (exactly) the
+        queries the tensor-core path flagged, return how many there were."""
+        pending = getattr(self, "_pending", None)
+        if pending is None:
+            return 0
+        queries, b, k, floor, item_offset, items, scores, counts, stream = pending
+        self._pending = None
+        redone = C.c_int(0)
+        _capi.check(
+            _capi.load().tav_finish_search(self._ix, C.c_void_p(queries.data_ptr()), b, k, C.c_float(floor),
+                                           item_offset, C.c_void_p(items.data_ptr()),
+                                           C.c_void_p(scores.data_ptr()), C.c_void_p(counts.data_ptr()),
+                                           C.c_void_p(stream), C.byref(redone))
+        )
+        return redone.value
