@@ -54,6 +54,15 @@ for st in $stages; do
     ncu_c5_list)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"tav|mma_topk|threshold|finalize|query_prep|scan_rows|select|merge" -c 60 --csv \
         --log-file gpurun_out/launches_c5.csv python bench.py --workload c5 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_c5_list.log 2>&1 ;;
+    sanitizer)
+      timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
+        -k "random_shapes or subset_duplicates or multi_pass or shard_merge or incremental" 2>&1 | tail -25 | tee gpurun_out/sanitizer_scan.log
+      timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_mma.py -m gpu -x -q \
+        -k "search_matches_oracle or in_register or fallback" 2>&1 | tail -25 | tee gpurun_out/sanitizer_mma.log
+      timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
+        -k "batched_equals or multi_pass" 2>&1 | tail -15 | tee gpurun_out/sanitizer_race.log ;;
+    hypo)
+      timeout 1200 python -m pytest tests/test_gpu_hypothesis.py -m gpu -x -q 2>&1 | tail -30 | tee gpurun_out/pytest_hypo.log ;;
     *) echo "unknown stage $st" ;;
   esac
 done
