@@ -62,7 +62,7 @@ enum tav_search_flags {
     TAV_QUERIES_ON_DEVICE = 1, /* `queries` is a device pointer (float32 [n_queries, dim]) */
     TAV_OUTPUTS_ON_DEVICE = 2, /* out_* are device pointers; no synchronisation */
     TAV_FORCE_SCAN = 4,        /* use the CUDA-core row-scan kernels whatever the shape */
-    TAV_FORCE_MMA = 8,         /* use the tcgen05 tensor-core kernel (bf16/fp16 storage only) */
+    TAV_FORCE_MMA = 8,         /* use the tcgen05 tensor-core kernel (needs dim % 8 == 0, no subset) */
     /* Fully asynchronous tensor-core search (needs both ..._ON_DEVICE flags): the check whether
      * some query must be redone by the exact row scan — a host synchronisation — is left to
      * tav_finish_search.  Until then the outputs of such (rare) queries are not final. */
@@ -147,7 +147,7 @@ int tav_merge_topk(int device, int n_lists, int n_queries, int k, const int64_t*
                    float* out_scores, int32_t* out_counts, void* stream);
 
 /* Verification aid for the tensor-core path: every raw dot product it computes,
- * out_device[n_queries, size] float32 (device memory), for bf16/fp16 indexes.  `flags` may
+ * out_device[n_queries, size] float32 (device memory); float32 indexes go through their fp16 planes.  `flags` may
  * carry TAV_QUERIES_ON_DEVICE.  Synchronises.  Not a hot-path entry point. */
 int tav_mma_scores(tav_index* ix, const float* queries, int n_queries, int flags, float* out_device,
                    void* stream);
@@ -160,7 +160,8 @@ int tav_set_timing(tav_index* ix, int enabled);
  * search's stream: `scan_ms` = the dominant kernel (row-scan kernel, or the MAIN launch of the
  * tcgen05 kernel; summed over query chunks), `total_ms` = first launch to last result byte on
  * device (both -1 when timing is off); `launches` = kernels launched; `path` = 1 row-scan
- * kernels, 2 tcgen05 kernel.  Synchronises when timing is on. */
+ * kernels, 2 tcgen05 kernel on bf16/fp16 rows, 3 tcgen05 kernel on a float32 index through
+ * its two fp16 planes (x = hi + lo/2048, ~2^-22 relative).  Synchronises when timing is on. */
 int tav_last_timing(tav_index* ix, float* scan_ms, float* total_ms, int* launches, int* path);
 
 /* Per-kernel durations of the last tav_search, in launch order (up to `capacity` entries;

@@ -132,10 +132,12 @@ def test_auto_path_selection():
     assert base.last_timing()["path"] == "scan"
     f32 = make_base(v, "float32", None)
     f32.fuzzy_lookup_embeddings(q, 5, 0.0)
+    assert f32.last_timing()["path"] == "mma_split"   # float32 rows through their two fp16 planes
+    f32.fuzzy_lookup_embeddings(q[:4], 5, 0.0)
     assert f32.last_timing()["path"] == "scan"
+    odd = make_base(O.make_corpus(5000, 100, seed=1)[0], "bfloat16", "mma")  # 200-byte rows: no TMA
     with pytest.raises(ValueError):
-        bad = make_base(v, "float32", "mma")
-        bad.fuzzy_lookup_embeddings(q, 5, 0.0)
+        odd.fuzzy_lookup_embeddings(O.make_corpus(20, 100, seed=2)[0], 5, 0.0)
 
 
 def test_fallback_when_the_sampled_threshold_cannot_decide():
@@ -189,3 +191,63 @@ def test_deferred_check_async_search_and_finish():
     same.search_device(qd, 9, 0.0, defer_check=True)
     with pytest.raises(RuntimeError, match="never finished"):
         same.finish_search()
+
+
+# ------------------------------------------------------------------ float32 index on tensor cores
+@pytest.mark.parametrize("n,d,b", [(256, 64, 128), (3001, 136, 130), (700, 1536, 256), (40000, 384, 64)])
+def test_split_every_dot_product_float32(n, d, b):
+    """float32 rows as two fp16 planes (x = hi + lo/2048): every dot vs float64 on the UNROUNDED data."""
+    v, q = O.make_corpus(n, d, seed=n + d + 1, n_queries=b)
+    base = make_base(v, "float32")
+    got = mma_scores(base, q)
+    want = q.astype(np.float64) @ v.astype(np.float64).T
+    np.testing.assert_allclose(got, want, atol=1e-6, rtol=0)
+    assert np.abs(got - want).max() < 5e-7
+
+
+@pytest.mark.parametrize("n,d,b,k,ms", [
+    (20000, 768, 64, 32, 0.0),
+    (50000, 384, 300, 5, 0.0),       # in-register top-k on the split form
+    (30000, 1536, 17, 100, 0.0),
+    (20011, 256, 33, 50, 0.52),
+    (6000, 128, 200, 10, 0.0),       # no sampling
+])
+def test_split_search_matches_reference_on_float32_inputs(n, d, b, k, ms):
+    """The north-star statement itself: identical float32 inputs, batched, on tensor cores."""
+    v, q = O.make_corpus(n, d, seed=n + b + 7, n_queries=b)
+    base = make_base(v, "float32", None)
+    batch = base.fuzzy_lookup_embeddings(q, max_hits=k, min_score=ms)
+    assert base.last_timing()["path"] == "mma_split"
+    for i in list(range(min(b, 10))) + [b - 1]:
+        assert_hits_match(batch[i], O.lookup(v, q[i], k, ms), min_score=ms, what=f"split q{i}")
+
+
+def test_split_planes_follow_appends_and_clear():
+    v, q = O.make_corpus(30000, 64, seed=3, n_queries=20)
+    base = make_base(v[:10000], "float32", None)
+    for got, qq in zip(base.fuzzy_lookup_embeddings(q, 10, 0.0), q):
+        assert_hits_match(got, O.lookup(v[:10000], qq, 10, 0.0))
+    base.add_embeddings(None, v[10000:30000])          # grows past the planes' capacity
+    for got, qq in zip(base.fuzzy_lookup_embeddings(q, 10, 0.0), q):
+        assert_hits_match(got, O.lookup(v, qq, 10, 0.0))
+    base.add_embedding(None, q[3])                      # one more row
+    assert base.fuzzy_lookup_embeddings(q, 1, 0.0)[3][0].item == 30000
+    base.clear()
+    base.add_embeddings(None, v[5000:12000])
+    for got, qq in zip(base.fuzzy_lookup_embeddings(q, 10, 0.0), q):
+        assert_hits_match(got, O.lookup(v[5000:12000], qq, 10, 0.0))
+    assert base.last_timing()["path"] == "mma_split"
+
+
+def test_split_values_beyond_fp16_range_fall_back_to_the_exact_scan():
+    v, q = O.make_corpus(8000, 64, seed=4, n_queries=20)
+    v = v.copy()
+    v[1234] *= 3.0e5                                     # |x| > 65504: the fp16 planes cannot hold it
+    base = make_base(v, "float32", None)
+    with np.errstate(over="ignore"):
+        for got, qq in zip(base.fuzzy_lookup_embeddings(q, 10, 0.0), q):
+            assert_hits_match(got, O.lookup(v, qq, 10, 0.0))
+    big_q = q * 1.0e6                                    # queries out of range as well
+    ok = make_base(O.make_corpus(8000, 64, seed=4)[0], "float32", None)
+    for got, qq in zip(ok.fuzzy_lookup_embeddings(big_q, 10, 0.0), big_q):
+        assert_hits_match(got, O.lookup(O.make_corpus(8000, 64, seed=4)[0], qq, 10, 0.0))

@@ -134,8 +134,15 @@ def test_batched_equals_single_and_oracle():
     assert len(batch) == 21
     for qq, got in zip(q, batch):
         assert_hits_match(got, O.lookup(v, qq, 15, 0.4), min_score=0.4)
+        # the batch takes the tensor-core form of the float32 index (21 queries, 6000 rows), the
+        # single lookup the row scan: two CUDA paths, same float32 inputs
         single = base.fuzzy_lookup_embedding(qq, max_hits=15, min_score=0.4)
-        assert [(h.item, h.score) for h in single] == [(h.item, h.score) for h in got]
+        assert_hits_match(single, got, score_tol=2e-6, min_score=0.4)
+    base.force_path = "scan"
+    for qq, got in zip(q, base.fuzzy_lookup_embeddings(q, max_hits=15, min_score=0.4)):
+        single = base.fuzzy_lookup_embedding(qq, max_hits=15, min_score=0.4)
+        assert [(h.item, h.score) for h in single] == [(h.item, h.score) for h in got]  # scan: bit-identical
+    base.force_path = None
     items, scores, counts = base.search_arrays(q, 15, 0.4)
     assert items.shape == (21, 15) and scores.dtype == np.float32 and counts.dtype == np.int32
     assert np.all(items[np.arange(15)[None, :] >= counts[:, None]] == -1)

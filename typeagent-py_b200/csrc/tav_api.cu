@@ -114,6 +114,13 @@ struct tav_index {
     DevBuf mma_ws;      // tensor-core path workspace
     DevBuf retry;       // int32 [n_queries] flags of the last tensor-core search + [1] running total at the end
     int retry_capacity = 0;      // queries the flag array is sized for
+    // float32 indexes: the rows as two fp16 planes for the tensor-core path (built lazily,
+    // extended on append); split_flag[0] = a corpus value left the fp16 range (sticky),
+    // split_flag[1] = a query value did (per search)
+    DevBuf split_hi, split_lo, split_flag;
+    int64_t split_rows = 0;      // rows [0, split_rows) of the planes are current
+    int64_t split_cap = 0;
+    bool last_split = false;     // the last tensor-core search used the planes
     int pending_queries = 0;     // > 0: a TAV_DEFER_RETRY search awaits tav_finish_search
 
     // timing of the last search
@@ -217,7 +224,7 @@ int tav_destroy(tav_index* ix) {
     cudaDeviceSynchronize();  // searches may still be in flight on the caller's streams
     if (ix->rows && !ix->adopted) cudaFree(ix->rows);
     for (DevBuf* b : {&ix->queries, &ix->subset, &ix->cand_keys, &ix->cand_count, &ix->out_pack,
-                      &ix->staging, &ix->mma_ws, &ix->retry})
+                      &ix->staging, &ix->mma_ws, &ix->retry, &ix->split_hi, &ix->split_lo, &ix->split_flag})
         b->release();
     ix->pin_in.release();
     ix->pin_out.release();
@@ -239,6 +246,7 @@ int tav_clear(tav_index* ix) {
         ix->capacity = 0;
     }
     ix->size = 0;
+    ix->split_rows = 0;
     return TAV_OK;
 }
 
@@ -348,6 +356,7 @@ int tav_adopt_device(tav_index* ix, void* device_rows, int64_t n, int dim) {
     }
     ix->dim = dim;
     ix->rows = device_rows;
+    ix->split_rows = 0;
     ix->adopted = true;
     ix->size = n;
     ix->capacity = n;
@@ -462,6 +471,43 @@ static int scan_search(tav_index* ix, const float* d_queries, int nq_total, int 
 
 }  // extern "C"
 
+// float32 index -> fp16 hi/lo planes covering rows [0, size); returns TAV_ERR_OOM when they do not fit
+static int ensure_split_planes(tav_index* ix, cudaStream_t s) {
+    const size_t plane_row = static_cast<size_t>(ix->dim) * 2;
+    if (ix->split_flag.bytes == 0) {
+        TAV_CUDA(ix->split_flag.ensure(2 * sizeof(int)));
+        TAV_CUDA(cudaMemsetAsync(ix->split_flag.p, 0, 2 * sizeof(int), s));
+    }
+    if (ix->size > ix->split_cap) {
+        const int64_t cap = std::max<int64_t>(ix->size, ix->capacity);
+        ix->split_hi.release();
+        ix->split_lo.release();
+        ix->split_cap = 0;
+        ix->split_rows = 0;
+        cudaError_t e1 = ix->split_hi.ensure(static_cast<size_t>(cap) * plane_row);
+        cudaError_t e2 = e1 == cudaSuccess ? ix->split_lo.ensure(static_cast<size_t>(cap) * plane_row) : e1;
+        if (e2 != cudaSuccess) {
+            cudaGetLastError();
+            ix->split_hi.release();
+            ix->split_lo.release();
+            set_error("not enough device memory for the fp16 planes of the float32 index");
+            return TAV_ERR_OOM;
+        }
+        ix->split_cap = cap;
+        TAV_CUDA(cudaMemsetAsync(ix->split_flag.p, 0, sizeof(int), s));
+    }
+    if (ix->split_rows < ix->size) {
+        const int64_t first = ix->split_rows, n = ix->size - first;
+        TAV_CUDA(launch_split_rows(static_cast<const float*>(ix->rows) + first * ix->dim,
+                                   static_cast<char*>(ix->split_hi.p) + static_cast<size_t>(first) * plane_row,
+                                   static_cast<char*>(ix->split_lo.p) + static_cast<size_t>(first) * plane_row, n,
+                                   ix->dim, static_cast<int*>(ix->split_flag.p), s));
+        ix->split_rows = ix->size;
+        ix->launches += 1;
+    }
+    return TAV_OK;
+}
+
 // Synchronising tail of a tensor-core search: read the retry flags, redo flagged queries exactly.
 static int resolve_retries(tav_index* ix, const float* d_queries, int n_queries, int k, float min_score,
                            int64_t item_offset, int64_t* d_items, float* d_scores, int32_t* d_counts,
@@ -472,20 +518,24 @@ static int resolve_retries(tav_index* ix, const float* d_queries, int n_queries,
                              cudaMemcpyDeviceToHost, s));
     TAV_CUDA(cudaMemcpyAsync(&host[n_queries], flags + ix->retry_capacity, sizeof(int32_t),
                              cudaMemcpyDeviceToHost, s));
+    int out_of_range[2] = {0, 0};  // split form: a corpus / query value beyond the fp16 range
+    if (ix->last_split)
+        TAV_CUDA(cudaMemcpyAsync(out_of_range, ix->split_flag.p, sizeof(out_of_range), cudaMemcpyDeviceToHost, s));
     TAV_CUDA(cudaStreamSynchronize(s));
     ix->pending_queries = 0;
+    const bool redo_all = out_of_range[0] != 0 || out_of_range[1] != 0;
     const int total = host[n_queries];
     int n_flagged = 0;
     for (int q = 0; q < n_queries; ++q) {
-        if (!host[q]) continue;
-        ++n_flagged;
+        if (host[q]) ++n_flagged;
+        if (!host[q] && !redo_all) continue;
         int rc = scan_search(ix, d_queries + static_cast<size_t>(q) * ix->dim, 1, k, min_score, nullptr,
                              ix->size, item_offset, d_items + static_cast<size_t>(q) * k,
                              d_scores + static_cast<size_t>(q) * k, d_counts + q, nullptr, s);
         if (rc != TAV_OK) return rc;
     }
     if (total != 0) TAV_CUDA(cudaMemsetAsync(flags + ix->retry_capacity, 0, sizeof(int32_t), s));
-    if (redone) *redone = n_flagged;
+    if (redone) *redone = redo_all ? n_queries : n_flagged;
     if (total != n_flagged) {
         set_error("%d queries of earlier deferred searches needed the exact fallback but were never finished",
                   total - n_flagged);
@@ -624,20 +674,35 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
     }
 
     // path choice: tensor cores for batches on 16-bit storage, row scan otherwise
-    bool use_mma = false;
-    if (!(flags & TAV_FORCE_SCAN) && !subset && mma_supported(ix->dtype, ix->dim) && k <= kPassK) {
+    bool use_mma = false, use_split = false;
+    const bool mma_able = mma_supported(ix->dtype, ix->dim) || (ix->dtype == TAV_F32 && mma_split_supported(ix->dim));
+    if (!(flags & TAV_FORCE_SCAN) && !subset && mma_able && k <= kPassK) {
         use_mma = (flags & TAV_FORCE_MMA) || (n_queries >= 16 && ix->size >= 4096);
+        use_split = use_mma && ix->dtype == TAV_F32;
     }
     if ((flags & TAV_FORCE_MMA) && !use_mma) {
-        set_error("tav_search: TAV_FORCE_MMA needs bf16/fp16 storage, dim %% 64 == 0, no subset, k <= %d", kPassK);
+        set_error("tav_search: TAV_FORCE_MMA needs dim %% 8 == 0, no subset, k <= %d", kPassK);
         return TAV_ERR_INVALID;
+    }
+    if (use_split) {
+        const int rc = ensure_split_planes(ix, s);
+        if (rc == TAV_ERR_OOM && !(flags & TAV_FORCE_MMA)) {
+            use_mma = use_split = false;  // a speed choice, not a correctness one: the exact row scan serves it
+        } else if (rc != TAV_OK) {
+            return rc;
+        }
     }
 
     if (use_mma) {
-        ix->path = 2;
+        ix->path = use_split ? 3 : 2;
+        ix->last_split = use_split;
         MmaArgs m{};
         m.device = ix->device;
-        m.corpus = ix->rows;
+        m.corpus = use_split ? ix->split_hi.p : ix->rows;
+        m.corpus_lo = use_split ? ix->split_lo.p : nullptr;
+        m.split = use_split ? 1 : 0;
+        m.split_overflow = use_split ? static_cast<int*>(ix->split_flag.p) + 1 : nullptr;
+        if (use_split) TAV_CUDA(cudaMemsetAsync(m.split_overflow, 0, sizeof(int), s));
         m.dtype = ix->dtype;
         m.n_corpus = ix->size;
         m.dim = ix->dim;
@@ -717,8 +782,9 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
 int tav_mma_scores(tav_index* ix, const float* queries, int n_queries, int flags, float* out_device,
                    void* stream) {
     if (!ix || n_queries < 1 || !queries || !out_device) return TAV_ERR_INVALID;
-    if (!mma_supported(ix->dtype, ix->dim) || ix->size == 0) {
-        set_error("tav_mma_scores: needs a non-empty bf16/fp16 index with dim %% 8 == 0");
+    const bool split = ix->dtype == TAV_F32;
+    if (ix->size == 0 || !(split ? mma_split_supported(ix->dim) : mma_supported(ix->dtype, ix->dim))) {
+        set_error("tav_mma_scores: needs a non-empty index with dim %% 8 == 0");
         return TAV_ERR_INVALID;
     }
     if (int rc = set_device(ix)) return rc;
@@ -730,9 +796,14 @@ int tav_mma_scores(tav_index* ix, const float* queries, int n_queries, int flags
         TAV_CUDA(cudaMemcpyAsync(ix->queries.p, queries, q_bytes, cudaMemcpyHostToDevice, s));
         d_queries = static_cast<const float*>(ix->queries.p);
     }
+    if (split)
+        if (int rc = ensure_split_planes(ix, s)) return rc;
     MmaArgs m{};
     m.device = ix->device;
-    m.corpus = ix->rows;
+    m.corpus = split ? ix->split_hi.p : ix->rows;
+    m.corpus_lo = split ? ix->split_lo.p : nullptr;
+    m.split = split ? 1 : 0;
+    m.split_overflow = split ? static_cast<int*>(ix->split_flag.p) + 1 : nullptr;
     m.dtype = ix->dtype;
     m.n_corpus = ix->size;
     m.dim = ix->dim;

@@ -60,12 +60,19 @@ cudaError_t launch_convert(const void* src, int src_dtype, void* dst, int dst_dt
 
 // ---- tensor-core path (tav_mma.cu) -----------------------------------------------------
 struct MmaPlan;  // opaque: tensor maps + workspace for one (index, batch shape)
-bool mma_supported(int dtype, int dim);
+bool mma_supported(int dtype, int dim);   // bf16 / fp16 storage
+bool mma_split_supported(int dim);        // float32 storage carried as two fp16 planes
+// float32 rows -> fp16 planes hi, lo with x ~= hi + lo / 2048; *overflow |= 1 if some |x| > fp16 range
+cudaError_t launch_split_rows(const float* src, void* hi, void* lo, int64_t n, int dim, int* overflow,
+                              cudaStream_t s);
 // returns cudaSuccess and fills outputs exactly like scan+select; see tav_mma.cu
 struct MmaArgs {
     int device;
-    const void* corpus;
-    int dtype;
+    const void* corpus;    // storage rows; for split float32 data: the hi plane (fp16)
+    const void* corpus_lo; // split only: the lo plane (fp16)
+    int split;             // 1: float32 index searched through its two fp16 planes
+    int* split_overflow;   // split only: device flag set when a value left the fp16 range
+    int dtype;             // storage dtype of the index (TAV_F32 when split)
     int64_t n_corpus;
     int dim;
     const float* queries;  // device float32 [nq, dim]

@@ -97,12 +97,6 @@ __device__ __forceinline__ void insert_top(float (&top)[kSampleTop], float x) {
     }
 }
 
-// CG = 1: one CTA per tile, up to 2 query blocks processed one after the other.
-// CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per tile: CTA r owns query block r
-//         (its 128 TMEM lanes) and stages rows [128r, 128r+128) of the corpus tile; every MMA is
-//         M=256 x N=256 across the pair, so each CTA's shared memory sees half of the operand
-//         traffic of the single-CTA form — the single-CTA form is smem-bandwidth bound at ~55 %
-//         of the tensor pipe (profiles/README.md).
 __device__ __forceinline__ void insert_key(uint64_t (&top)[kRegK], uint64_t key) {
     // top[] sorted descending; key > top[last] on entry
 #pragma unroll
@@ -113,13 +107,29 @@ __device__ __forceinline__ void insert_key(uint64_t (&top)[kRegK], uint64_t key)
     }
 }
 
-template <int MODE, int CG>
+// CG = 1: one CTA per tile, up to 2 query blocks processed one after the other.
+// CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per tile: CTA r owns query block r
+//         (its 128 TMEM lanes) and stages rows [128r, 128r+128) of the corpus tile; every MMA is
+//         M=256 x N=256 across the pair, so each CTA's shared memory sees half of the operand
+//         traffic of the single-CTA form — the single-CTA form is smem-bandwidth bound at ~55 %
+//         of the tensor pipe (profiles/README.md).
+// SPLIT: float32 data carried as two fp16 planes, x = hi + lo / 2048 (22 significant bits;
+//         products of fp16 values are exact in the fp32 accumulator).  Three MMAs per K step:
+//         hi.hi' into the MAIN accumulator, hi.lo' + lo.hi' into the CROSS accumulator; the
+//         epilogue combines main + cross / 2048 (the lo.lo' term, <= 2^-22 relative, is dropped).
+//         Both accumulators of a tile fill TMEM (2 x 256 columns), so tiles are not
+//         double-buffered in this form.
+template <int MODE, int CG, bool SPLIT>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
+                const __grid_constant__ CUtensorMap map_q_lo, const __grid_constant__ CUtensorMap map_c_lo,
                 const KernelArgs a, const uint32_t idesc) {
     constexpr int kRowsB = kBN / CG;                         // corpus rows staged per CTA per tile
-    constexpr int kStageBytesCta = kABytes + kRowsB * kBK * 2;
-    constexpr int kNumStages = CG == 2 ? 6 : 4;              // 6 x 32 KB or 4 x 48 KB
+    constexpr int kBBytesCta = kRowsB * kBK * 2;
+    constexpr int kPlanes = SPLIT ? 2 : 1;
+    constexpr int kStageBytesCta = kPlanes * (kABytes + kBBytesCta);  // [A | B | A_lo | B_lo]
+    constexpr int kNumStages = (CG == 2 ? 6 : 4) / kPlanes;  // 192 KB of tiles in every form
+    constexpr int kAccStages = SPLIT ? 1 : 2;                // TMEM accumulator stages
     extern __shared__ uint8_t smem_dyn[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -152,6 +162,10 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         ptx::fence_mbar_init();
         ptx::prefetch_tensormap(&map_q);
         ptx::prefetch_tensormap(&map_c);
+        if (SPLIT) {
+            ptx::prefetch_tensormap(&map_q_lo);
+            ptx::prefetch_tensormap(&map_c_lo);
+        }
     }
     if (warp == 1) {
         if (CG == 2) ptx::tmem_alloc_pair(tmem_slot, kTmemCols);
@@ -184,10 +198,20 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                             if (cta_rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * kStageBytesCta);
                             ptx::tma_load_2d_pair(sa, &map_q, lead_full, kb * kBK, m * kBM, ptx::kEvictLast);
                             ptx::tma_load_2d_pair(sa + kABytes, &map_c, lead_full, kb * kBK, row0, ptx::kEvictFirst);
+                            if (SPLIT) {
+                                uint8_t* sl = sa + kABytes + kBBytesCta;
+                                ptx::tma_load_2d_pair(sl, &map_q_lo, lead_full, kb * kBK, m * kBM, ptx::kEvictLast);
+                                ptx::tma_load_2d_pair(sl + kABytes, &map_c_lo, lead_full, kb * kBK, row0, ptx::kEvictFirst);
+                            }
                         } else {
                             ptx::mbar_expect_tx(&full[stage], kStageBytesCta);
                             ptx::tma_load_2d(sa, &map_q, &full[stage], kb * kBK, m * kBM, ptx::kEvictLast);
                             ptx::tma_load_2d(sa + kABytes, &map_c, &full[stage], kb * kBK, row0, ptx::kEvictFirst);
+                            if (SPLIT) {
+                                uint8_t* sl = sa + kABytes + kBBytesCta;
+                                ptx::tma_load_2d(sl, &map_q_lo, &full[stage], kb * kBK, m * kBM, ptx::kEvictLast);
+                                ptx::tma_load_2d(sl + kABytes, &map_c_lo, &full[stage], kb * kBK, row0, ptx::kEvictFirst);
+                            }
                         }
                         if (++stage == kNumStages) {
                             stage = 0;
@@ -203,10 +227,11 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             uint32_t stage = 0, phase = 0, item = 0;
             for (int w = unit; w < a.n_work; w += n_units) {
                 for (int mb = 0; mb < n_mblocks; ++mb, ++item) {
-                    const uint32_t as = item & 1, aphase = (item >> 1) & 1;
+                    const uint32_t as = item % kAccStages, aphase = (item / kAccStages) & 1;
                     ptx::mbar_wait(&tempty[as], aphase ^ 1);  // epilogue(s) drained this accumulator
                     ptx::tc_fence_after();
                     const uint32_t d_tmem = tmem_base + as * kBN;
+                    const uint32_t d_cross = tmem_base + kBN;  // SPLIT only
                     for (int kb = 0; kb < a.kb_count; ++kb) {
                         ptx::mbar_wait(&full[stage], phase);
                         ptx::tc_fence_after();
@@ -217,8 +242,20 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                         for (int k = 0; k < kBK / kUmmaK; ++k) {
                             // advance 16 elements = 32 bytes along K inside the swizzle atom
                             const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
-                            if (CG == 2) ptx::umma_f16_pair(d_tmem, da + koff, db + koff, idesc, (kb | k) != 0 ? 1u : 0u);
-                            else ptx::umma_f16(d_tmem, da + koff, db + koff, idesc, (kb | k) != 0 ? 1u : 0u);
+                            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                            if (CG == 2) ptx::umma_f16_pair(d_tmem, da + koff, db + koff, idesc, acc);
+                            else ptx::umma_f16(d_tmem, da + koff, db + koff, idesc, acc);
+                            if (SPLIT) {
+                                const uint64_t da_lo = ptx::make_kmajor_sw128_desc(sa + kABytes + kBBytesCta) + koff;
+                                const uint64_t db_lo = ptx::make_kmajor_sw128_desc(sa + 2 * kABytes + kBBytesCta) + koff;
+                                if (CG == 2) {
+                                    ptx::umma_f16_pair(d_cross, da + koff, db_lo, idesc, acc);  // hi . lo'
+                                    ptx::umma_f16_pair(d_cross, da_lo, db + koff, idesc, 1u);   // lo . hi'
+                                } else {
+                                    ptx::umma_f16(d_cross, da + koff, db_lo, idesc, acc);
+                                    ptx::umma_f16(d_cross, da_lo, db + koff, idesc, 1u);
+                                }
+                            }
                         }
                         // smem slot reusable (in both CTAs) once these MMAs retire
                         if (CG == 2) ptx::umma_commit_pair(&empty[stage], 3);
@@ -263,7 +300,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
             for (int mb = 0; mb < kMaxMT; ++mb) {
                 if (mb >= n_mblocks) break;
-                const uint32_t as = item & 1, aphase = (item >> 1) & 1;
+                const uint32_t as = item % kAccStages, aphase = (item / kAccStages) & 1;
                 ++item;
                 const int m = CG == 2 ? static_cast<int>(cta_rank) : mb;
                 const int q = m * kBM + lane_q;
@@ -331,20 +368,34 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     }
                 };
 
-                // two register buffers: the load of chunk c+1 is in flight while chunk c is screened
                 uint32_t va[32], vb[32];
-                if (ncols > 0) {
-                    ptx::tmem_ld_32x32(taddr, va);
-                    ptx::tmem_ld_wait();
-                }
+                if (SPLIT) {
+                    // main and cross accumulators of the same 32 columns, combined: x = main + cross / 2048
 #pragma unroll 1
-                for (int c0 = 0; c0 < kEpiCols; c0 += 64) {
-                    if (c0 + 32 < ncols) ptx::tmem_ld_32x32(taddr + c0 + 32, vb);
-                    if (c0 < ncols) process(va, c0);
-                    ptx::tmem_ld_wait();
-                    if (c0 + 64 < ncols) ptx::tmem_ld_32x32(taddr + c0 + 64, va);
-                    if (c0 + 32 < ncols) process(vb, c0 + 32);
-                    ptx::tmem_ld_wait();
+                    for (int c0 = 0; c0 < ncols; c0 += 32) {
+                        ptx::tmem_ld_32x32(taddr + c0, va);
+                        ptx::tmem_ld_32x32(taddr + kBN + c0, vb);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            va[i] = __float_as_uint(fmaf(__uint_as_float(vb[i]), 1.0f / 2048.0f, __uint_as_float(va[i])));
+                        process(va, c0);
+                    }
+                } else {
+                    // two register buffers: the load of chunk c+1 is in flight while chunk c is screened
+                    if (ncols > 0) {
+                        ptx::tmem_ld_32x32(taddr, va);
+                        ptx::tmem_ld_wait();
+                    }
+#pragma unroll 1
+                    for (int c0 = 0; c0 < kEpiCols; c0 += 64) {
+                        if (c0 + 32 < ncols) ptx::tmem_ld_32x32(taddr + c0 + 32, vb);
+                        if (c0 < ncols) process(va, c0);
+                        ptx::tmem_ld_wait();
+                        if (c0 + 64 < ncols) ptx::tmem_ld_32x32(taddr + c0 + 64, va);
+                        if (c0 + 32 < ncols) process(vb, c0 + 32);
+                        ptx::tmem_ld_wait();
+                    }
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -423,6 +474,25 @@ __global__ void query_prep_kernel(const float* q, T* out, int nq, int nq_pad, in
         const float v = row < nq ? q[i] : 0.0f;
         store_rn(out + i, v);
     }
+}
+
+// float32 x -> fp16 planes hi = fp16(x), lo = fp16((x - hi) * 2048): x ~= hi + lo / 2048 to 2^-22.
+// Rows >= n_valid are zero-filled (query padding).  |x| must be below the fp16 range; a value
+// that is not sets *overflow and the caller redoes the search with the exact row scan.
+__global__ void split_rows_kernel(const float* src, __half* hi, __half* lo, int64_t n_valid, int64_t n_total,
+                                  int dim, int* overflow) {
+    const int64_t total = n_total * dim;
+    bool bad = false;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float x = (i / dim) < n_valid ? src[i] : 0.0f;
+        const __half h = __float2half_rn(x);
+        const float rest = __fmul_rn(__fsub_rn(x, __half2float(h)), 2048.0f);
+        hi[i] = h;
+        lo[i] = __float2half_rn(rest);
+        bad |= fabsf(x) > 60000.0f;
+    }
+    if (bad) atomicOr(overflow, 1);
 }
 
 // One WARP per query: the kSampleTop-th largest sampled dot -> admission threshold; also resets
@@ -650,7 +720,7 @@ struct Plan {
     uint32_t capg;
     int nq_pad;        // all queries, padded to 128
     // workspace offsets
-    size_t off_q, off_sample, off_thr, off_floor, off_count, off_cand, total;
+    size_t off_q, off_q_lo, off_sample, off_thr, off_floor, off_count, off_cand, total;
     bool reg_top;      // k <= kRegK: in-register top-k, no sampling / candidate buffers
 };
 
@@ -683,6 +753,8 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
     size_t off = 0;
     p.off_q = off;
     off = align(off + static_cast<size_t>(p.nq_pad) * dim * 2);
+    p.off_q_lo = off;  // lo plane of the queries (split form only; reserved always)
+    off = align(off + static_cast<size_t>(p.nq_pad) * dim * 2);
     p.off_sample = off;  // SAMPLE lists (float x kSampleTop) or REGTOP lists (u64 x kRegK), per unit and half
     off = align(off + static_cast<size_t>(std::max(p.sample_ctas, p.reg_top ? p.main_ctas : 0)) * 2 * kChunkQueries *
                           std::max(kSampleTop * sizeof(float), kRegK * sizeof(uint64_t)));
@@ -698,10 +770,15 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
     return p;
 }
 
-template <int MODE, int CG>
-cudaError_t launch_kernel_cg(const CUtensorMap& mq, const CUtensorMap& mc, const KernelArgs& ka, uint32_t idesc,
-                             int units, cudaStream_t s) {
-    auto kern = mma_topk_kernel<MODE, CG>;
+struct Maps {
+    CUtensorMap q, q_lo;        // queries (hi plane / lo plane when split)
+    CUtensorMap c1, c1_lo;      // corpus, 256-row boxes (single CTA)
+    CUtensorMap c2, c2_lo;      // corpus, 128-row boxes (per CTA of a pair)
+};
+
+template <int MODE, int CG, bool SPLIT>
+cudaError_t launch_kernel_cg(const Maps& m, const KernelArgs& ka, uint32_t idesc, int units, cudaStream_t s) {
+    auto kern = mma_topk_kernel<MODE, CG, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(kSmemBytes));
     if (e != cudaSuccess) return e;
@@ -717,21 +794,30 @@ cudaError_t launch_kernel_cg(const CUtensorMap& mq, const CUtensorMap& mc, const
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, mq, mc, ka, idesc);
+    if (CG == 2) return cudaLaunchKernelEx(&cfg, kern, m.q, m.c2, m.q_lo, m.c2_lo, ka, idesc);
+    return cudaLaunchKernelEx(&cfg, kern, m.q, m.c1, m.q_lo, m.c1_lo, ka, idesc);
 }
 
-// mt == 2 (129..256 queries): CTA pairs; mt == 1: single CTAs
+// mt == 2 (129..256 queries): CTA pairs; mt == 1: single CTAs; split: two-plane fp16 (float32 data)
 template <int MODE>
-cudaError_t launch_kernel(const CUtensorMap& mq, const CUtensorMap& mc1, const CUtensorMap& mc2,
-                          const KernelArgs& ka, int dtype, int units, cudaStream_t s) {
+cudaError_t launch_kernel(const Maps& m, const KernelArgs& ka, int dtype, bool split, int units, cudaStream_t s) {
     const int fmt = dtype == TAV_BF16 ? 1 : 0;
-    if (ka.mt == 2) return launch_kernel_cg<MODE, 2>(mq, mc2, ka, ptx::make_idesc_f16(2 * kBM, kBN, fmt), units, s);
-    return launch_kernel_cg<MODE, 1>(mq, mc1, ka, ptx::make_idesc_f16(kBM, kBN, fmt), units, s);
+    const uint32_t idesc = ptx::make_idesc_f16(ka.mt == 2 ? 2 * kBM : kBM, kBN, fmt);
+    if (ka.mt == 2)
+        return split ? launch_kernel_cg<MODE, 2, true>(m, ka, idesc, units, s)
+                     : launch_kernel_cg<MODE, 2, false>(m, ka, idesc, units, s);
+    return split ? launch_kernel_cg<MODE, 1, true>(m, ka, idesc, units, s)
+                 : launch_kernel_cg<MODE, 1, false>(m, ka, idesc, units, s);
 }
 
-cudaError_t prep_queries(const MmaArgs& a, void* dst, int nq_pad, cudaStream_t s) {
+cudaError_t prep_queries(const MmaArgs& a, void* dst, void* dst_lo, int nq_pad, cudaStream_t s) {
     const int64_t total = static_cast<int64_t>(nq_pad) * a.dim;
     const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 8));
+    if (a.split) {
+        split_rows_kernel<<<grid, 256, 0, s>>>(a.queries, static_cast<__half*>(dst), static_cast<__half*>(dst_lo),
+                                               a.nq, nq_pad, a.dim, a.split_overflow);
+        return cudaGetLastError();
+    }
     if (a.dtype == TAV_BF16)
         query_prep_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(a.queries, static_cast<__nv_bfloat16*>(dst), a.nq,
                                                               nq_pad, a.dim);
@@ -745,18 +831,53 @@ cudaError_t prep_queries(const MmaArgs& a, void* dst, int nq_pad, cudaStream_t s
 bool mma_supported(int dtype, int dim) {
     return (dtype == TAV_BF16 || dtype == TAV_F16) && dim >= 8 && dim % 8 == 0;
 }
+bool mma_split_supported(int dim) { return dim >= 8 && dim % 8 == 0; }
+
+cudaError_t launch_split_rows(const float* src, void* hi, void* lo, int64_t n, int dim, int* overflow,
+                              cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const int64_t total = n * dim;
+    const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));
+    split_rows_kernel<<<grid, 256, 0, s>>>(src, static_cast<__half*>(hi), static_cast<__half*>(lo), n, n, dim, overflow);
+    return cudaGetLastError();
+}
+
+namespace {
+// storage dtype the tensor-core kernel sees: fp16 planes for split float32 data
+inline int mma_dtype(const MmaArgs& a) { return a.split ? TAV_F16 : a.dtype; }
+
+bool build_corpus_maps(const MmaArgs& a, Maps& m) {
+    const int dt = mma_dtype(a);
+    if (!encode_map(&m.c1, dt, a.corpus, a.n_corpus, a.dim, kBN)) return false;
+    if (!encode_map(&m.c2, dt, a.corpus, a.n_corpus, a.dim, kBN / 2)) return false;
+    const void* lo = a.split ? a.corpus_lo : a.corpus;  // unused maps still need a valid encoding
+    if (!encode_map(&m.c1_lo, dt, lo, a.n_corpus, a.dim, kBN)) return false;
+    return encode_map(&m.c2_lo, dt, lo, a.n_corpus, a.dim, kBN / 2);
+}
+bool build_query_maps(const MmaArgs& a, const void* d_q, const void* d_q_lo, int q0, int mt, Maps& m) {
+    const int dt = mma_dtype(a);
+    const size_t off = static_cast<size_t>(q0) * a.dim * 2;
+    if (!encode_map(&m.q, dt, static_cast<const char*>(d_q) + off, mt * kBM, a.dim, kBM)) return false;
+    const void* lo = a.split ? d_q_lo : d_q;
+    return encode_map(&m.q_lo, dt, static_cast<const char*>(lo) + off, mt * kBM, a.dim, kBM);
+}
+bool args_ok(const MmaArgs& a) {
+    if (a.n_corpus >= (1ll << 31) || reinterpret_cast<uintptr_t>(a.corpus) % 16 != 0) return false;
+    if (a.split) return a.dtype == TAV_F32 && mma_split_supported(a.dim) && a.corpus_lo && a.split_overflow;
+    return mma_supported(a.dtype, a.dim);
+}
+}  // namespace
 
 size_t mma_workspace_bytes(const MmaArgs& a) { return make_plan(a.device, a.n_corpus, a.dim, a.nq, a.k).total; }
 
 cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s,
                               int* launches) {
-    if (!mma_supported(a.dtype, a.dim) || a.k > kPassK || a.n_corpus >= (1ll << 31) ||
-        reinterpret_cast<uintptr_t>(a.corpus) % 16 != 0)
-        return cudaErrorInvalidValue;
+    if (!args_ok(a) || a.k > kPassK) return cudaErrorInvalidValue;
     const Plan p = make_plan(a.device, a.n_corpus, a.dim, a.nq, a.k);
     if (workspace_bytes < p.total) return cudaErrorInvalidValue;
     char* ws = static_cast<char*>(workspace);
     void* d_q = ws + p.off_q;
+    void* d_q_lo = ws + p.off_q_lo;
     float* d_sample = reinterpret_cast<float*>(ws + p.off_sample);
     float* d_thr = reinterpret_cast<float*>(ws + p.off_thr);
     float* d_floor = reinterpret_cast<float*>(ws + p.off_floor);
@@ -764,21 +885,20 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
     uint64_t* d_cand = reinterpret_cast<uint64_t*>(ws + p.off_cand);
     int n_launch = 0;
 
-    cudaError_t e = prep_queries(a, d_q, p.nq_pad, s);
+    cudaError_t e = prep_queries(a, d_q, d_q_lo, p.nq_pad, s);
     if (e != cudaSuccess) return e;
     ++n_launch;
 
-    CUtensorMap map_c1, map_c2;  // corpus tile boxes: 256 rows (single CTA) / 128 rows (per CTA of a pair)
-    if (!encode_map(&map_c1, a.dtype, a.corpus, a.n_corpus, a.dim, kBN)) return cudaErrorUnknown;
-    if (!encode_map(&map_c2, a.dtype, a.corpus, a.n_corpus, a.dim, kBN / 2)) return cudaErrorUnknown;
+    Maps maps;
+    if (!build_corpus_maps(a, maps)) return cudaErrorUnknown;
+    const int kdt = mma_dtype(a);
+    const bool split = a.split != 0;
 
     int ev_used = 0;
     for (int q0 = 0; q0 < a.nq; q0 += kChunkQueries) {
         const int nq = std::min(kChunkQueries, a.nq - q0);
         const int mt = (nq + kBM - 1) / kBM;
-        CUtensorMap map_q;
-        const char* qbase = static_cast<const char*>(d_q) + static_cast<size_t>(q0) * a.dim * 2;
-        if (!encode_map(&map_q, a.dtype, qbase, mt * kBM, a.dim, kBM)) return cudaErrorUnknown;
+        if (!build_query_maps(a, d_q, d_q_lo, q0, mt, maps)) return cudaErrorUnknown;
 
         KernelArgs ka{};
         ka.n_rows = a.n_corpus;
@@ -810,7 +930,7 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
             ka.reg_top = reinterpret_cast<uint64_t*>(d_sample);
             ka.floor_score = a.floor_score;
             if ((e = ev_begin()) != cudaSuccess) return e;
-            e = launch_kernel<kRegTop>(map_q, map_c1, map_c2, ka, a.dtype, std::min(main_units, 160), s);
+            e = launch_kernel<kRegTop>(maps, ka, kdt, split, std::min(main_units, 160), s);
             if (e != cudaSuccess) return e;
             if ((e = ev_end(0)) != cudaSuccess) return e;
             ++n_launch;
@@ -829,7 +949,7 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
             ka.tile_mul = p.n_tiles;
             ka.tile_div = p.n_sample;
             if ((e = ev_begin()) != cudaSuccess) return e;
-            e = launch_kernel<kSample>(map_q, map_c1, map_c2, ka, a.dtype, sample_units, s);
+            e = launch_kernel<kSample>(maps, ka, kdt, split, sample_units, s);
             if (e != cudaSuccess) return e;
             if ((e = ev_end(1)) != cudaSuccess) return e;
             ++n_launch;
@@ -846,7 +966,7 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
         ka.tile_mul = 1;
         ka.tile_div = 1;
         if ((e = ev_begin()) != cudaSuccess) return e;
-        e = launch_kernel<kMain>(map_q, map_c1, map_c2, ka, a.dtype, main_units, s);
+        e = launch_kernel<kMain>(maps, ka, kdt, split, main_units, s);
         if (e != cudaSuccess) return e;
         if ((e = ev_end(0)) != cudaSuccess) return e;
         ++n_launch;
@@ -870,22 +990,20 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
 
 // Debug / verification entry: all raw dot products of the tensor-core path, out[nq, n_rows] (device).
 cudaError_t launch_mma_dump(const MmaArgs& a, void* workspace, size_t workspace_bytes, float* out, cudaStream_t s) {
-    if (!mma_supported(a.dtype, a.dim) || a.n_corpus >= (1ll << 31)) return cudaErrorInvalidValue;
+    if (!args_ok(a)) return cudaErrorInvalidValue;
     const Plan p = make_plan(a.device, a.n_corpus, a.dim, a.nq, 1);
     if (workspace_bytes < p.total) return cudaErrorInvalidValue;
     char* ws = static_cast<char*>(workspace);
     void* d_q = ws + p.off_q;
-    cudaError_t e = prep_queries(a, d_q, p.nq_pad, s);
+    void* d_q_lo = ws + p.off_q_lo;
+    cudaError_t e = prep_queries(a, d_q, d_q_lo, p.nq_pad, s);
     if (e != cudaSuccess) return e;
-    CUtensorMap map_c1, map_c2;
-    if (!encode_map(&map_c1, a.dtype, a.corpus, a.n_corpus, a.dim, kBN)) return cudaErrorUnknown;
-    if (!encode_map(&map_c2, a.dtype, a.corpus, a.n_corpus, a.dim, kBN / 2)) return cudaErrorUnknown;
+    Maps maps;
+    if (!build_corpus_maps(a, maps)) return cudaErrorUnknown;
     for (int q0 = 0; q0 < a.nq; q0 += kChunkQueries) {
         const int nq = std::min(kChunkQueries, a.nq - q0);
         const int mt = (nq + kBM - 1) / kBM;
-        CUtensorMap map_q;
-        const char* qbase = static_cast<const char*>(d_q) + static_cast<size_t>(q0) * a.dim * 2;
-        if (!encode_map(&map_q, a.dtype, qbase, mt * kBM, a.dim, kBM)) return cudaErrorUnknown;
+        if (!build_query_maps(a, d_q, d_q_lo, q0, mt, maps)) return cudaErrorUnknown;
         KernelArgs ka{};
         ka.n_rows = a.n_corpus;
         ka.kb_count = p.kb_count;
@@ -896,7 +1014,7 @@ cudaError_t launch_mma_dump(const MmaArgs& a, void* workspace, size_t workspace_
         ka.tile_div = 1;
         ka.dump = out + static_cast<size_t>(q0) * a.n_corpus;
         const int max_units = mt == 2 ? std::max(1, p.sms / 2) : p.sms;
-        e = launch_kernel<kDump>(map_q, map_c1, map_c2, ka, a.dtype, std::min(p.n_tiles, max_units), s);
+        e = launch_kernel<kDump>(maps, ka, mma_dtype(a), a.split != 0, std::min(p.n_tiles, max_units), s);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;

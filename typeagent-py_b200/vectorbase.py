@@ -399,7 +399,7 @@ class VectorBase:
         names = {0: "main", 1: "sample", 2: "aux"}
         breakdown = [(names.get(kinds[i], "?"), ms[i]) for i in range(min(n.value, 64))]
         return {"scan_ms": scan.value, "total_ms": total.value, "launches": launches.value,
-                "path": {1: "scan", 2: "mma"}.get(path.value, "none"), "kernels": breakdown}
+                "path": {1: "scan", 2: "mma", 3: "mma_split"}.get(path.value, "none"), "kernels": breakdown}
 
     # ------------------------------------------------------------------ lookups
     @staticmethod
