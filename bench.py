@@ -46,6 +46,10 @@ WORKLOADS = {
                desc="10M x 1536 fp16 row-sharded, batch 1024, top-100"),
     "c5": dict(rows=50_000, dim=384, storage="bfloat16", batch=1000, k=5, min_score=0.0,
                desc="RelatedTerms 50k x 384, 1000 query terms, top-5"),
+    "c5f32": dict(rows=50_000, dim=384, storage="float32", batch=1000, k=5, min_score=0.0,
+                  desc="RelatedTerms 50k x 384 float32 (as the reference stores it), 1000 query terms, top-5"),
+    "c2f32": dict(rows=1_000_000, dim=768, storage="float32", batch=64, k=32, min_score=0.0,
+                  desc="1M x 768 float32, batch 64, top-32 (split-precision tensor path)"),
 }
 ELEM = {"float32": 4, "bfloat16": 2, "float16": 2}
 
@@ -453,7 +457,7 @@ def run_b200(args, w):
     qps = batch / (ms_step / 1e3)
     e2e_ms_step = ms_e2e / args.steps
     # per-GPU dominant kernel: this rank's shard is read once per pass of the kernel
-    passes = 1 if path == "mma" else -(-batch // 8)
+    passes = 1 if path in ("mma", "mma_split") else -(-batch // 8)
     algo_bytes = algorithmic_bytes(hi - lo, dim, storage, batch, k)
     algo_launch_bytes = (hi - lo) * dim * ELEM[storage] * passes + batch * dim * 4 + batch * k * 12
     achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
@@ -472,7 +476,7 @@ def run_b200(args, w):
                 "api": "VectorBase.search_arrays(host float32 queries) -> host int64/float32 hits"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {
-            "bound": "hbm", "kernel": "scan_rows_kernel" if path == "scan" else "mma_topk_kernel",
+            "bound": "hbm", "kernel": "scan_rows_kernel" if path == "scan" else "mma_topk_kernel (" + path + ")",
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
             "of": peaks["source"], "traffic": None, "kernel_ms_per_step": kernel_ms,
             "per_step_ms_by_kernel_kind": breakdown,

@@ -23,6 +23,10 @@ for st in $stages; do
       timeout 900 python bench.py --steps 40 --warmup 5 2>gpurun_out/bench_c3.err | tee gpurun_out/bench_c3.json ;;
     tests_mma)
       timeout 600 python -m pytest tests/test_gpu_mma.py -m gpu -x -q 2>&1 | tail -40 | tee gpurun_out/pytest_mma.log ;;
+    bench_c5f32)
+      timeout 600 python bench.py --workload c5f32 --steps 10 --warmup 3 2>gpurun_out/bench_c5f32.err | tee gpurun_out/bench_c5f32.json ;;
+    bench_c2f32)
+      timeout 600 python bench.py --workload c2f32 --steps 10 --warmup 3 2>gpurun_out/bench_c2f32.err | tee gpurun_out/bench_c2f32.json ;;
     bench_c5)
       timeout 600 python bench.py --workload c5 --steps 10 --warmup 3 2>gpurun_out/bench_c5.err | tee gpurun_out/bench_c5.json ;;
     ncu_c1)
@@ -61,6 +65,12 @@ for st in $stages; do
         -k "search_matches_oracle or in_register or fallback" 2>&1 | tail -25 | tee gpurun_out/sanitizer_mma.log
       timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
         -k "batched_equals or multi_pass" 2>&1 | tail -15 | tee gpurun_out/sanitizer_race.log ;;
+    shard8)
+      timeout 600 python bench.py --rows 1250000 --steps 40 --warmup 5 --no-cpu-baseline 2>gpurun_out/bench_shard8.err | tee gpurun_out/bench_shard8.json
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:mma_topk -s 3 -c 1 \
+        -o gpurun_out/prof_shard8 -f python bench.py --rows 1250000 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_shard8.log 2>&1 ;;
+    latency)
+      timeout 600 python tools/latency_probe.py 2>&1 | tail -8 | tee gpurun_out/latency_probe.log ;;
     hypo)
       timeout 1200 python -m pytest tests/test_gpu_hypothesis.py -m gpu -x -q 2>&1 | tail -30 | tee gpurun_out/pytest_hypo.log ;;
     *) echo "unknown stage $st" ;;

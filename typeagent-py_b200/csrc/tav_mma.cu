@@ -331,17 +331,25 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
                     const uint32_t rbase = static_cast<uint32_t>(row0 + c0);
                     if (MODE == kMain) {
-                        // admitted rows are rare (one compare + predicated branch each): stays in registers
+                        // Slow path, taken only when the chunk holds an admitted row: branch-free mask of
+                        // the admitted columns, ONE atomicAdd per lane for all of them (the warp's lanes
+                        // issue theirs together: one round trip per chunk instead of one per admitted
+                        // row — the per-row form made the epilogue the bottleneck on small shards, where
+                        // admitted rows are dense; profiles/README.md), then predicated stores.
                         const float t = tau[mb];
                         if (mx >= t) {
+                            uint32_t mask = 0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                mask |= (__uint_as_float(v[i]) >= t && i < nvalid) ? (1u << i) : 0u;
+                            const uint32_t c = __popc(mask);
+                            uint32_t slot = c ? atomicAdd(&a.cand_count[q], c) : 0u;
+                            uint64_t* dst = a.cand + static_cast<size_t>(q) * a.capg;
 #pragma unroll
                             for (int i = 0; i < 32; ++i) {
-                                const float x = __uint_as_float(v[i]);
-                                if (x >= t && i < nvalid) {
-                                    const uint32_t slot = atomicAdd(&a.cand_count[q], 1u);
-                                    if (slot < a.capg)
-                                        a.cand[static_cast<size_t>(q) * a.capg + slot] =
-                                            (static_cast<uint64_t>(v[i]) << 32) | (rbase + i);
+                                if ((mask >> i) & 1u) {
+                                    if (slot < a.capg) dst[slot] = (static_cast<uint64_t>(v[i]) << 32) | (rbase + i);
+                                    ++slot;
                                 }
                             }
                         }
@@ -734,10 +742,12 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
     // Rows we aim to admit per query.  The threshold is the m-th largest (m = kSampleTop) of a
     // uniform sample of S = m*N/target rows, so about `target` rows of the corpus lie above it.
     // Starvation (< k admitted) needs m of the corpus' top k inside the sample — expected k*m/target
-    // = 0.4 for k = 100: probability ~1e-9; overflow (> 8*target) is rarer still.  Either way the
-    // query is merely redone by the exact row scan.
-    // Small corpora aim lower (1/64 of the rows) so that the MAIN epilogue's slow path stays rare.
-    const int64_t target = std::max<int64_t>(16ll * k, std::min<int64_t>(2048, n_rows / 64));
+    // <= 1: probability <= 1e-5 per query; overflow (> 8*target) is rarer still.  Either way the query
+    // is merely redone by the exact row scan.
+    // 8k keeps starvation at ~1e-5 per query (Poisson(1) >= 8); small corpora aim lower (1/4096 of
+    // the rows, never below 512) so that admitted rows stay sparse in the MAIN epilogue.
+    const int64_t target =
+        std::max<int64_t>(std::max<int64_t>(8ll * k, 512), std::min<int64_t>(2048, n_rows / 4096));
     if (n_rows <= 16384 || 8 * target >= n_rows) {
         p.n_sample = 0;
         p.capg = static_cast<uint32_t>(n_rows);
