@@ -82,8 +82,11 @@ __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_cluster_addr
                  "r"(bytes)
                  : "memory");
 }
+// Default semantics (release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id): the TMEM reads
+// this arrive publishes are already complete (tcgen05.wait::ld + fence::before_thread_sync), so no
+// cluster-scope memory fence is needed — `.release.cluster` here cost an ERRBAR + CGAERRBAR per tile.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 
 // ---- TMA -----------------------------------------------------------------------------------
