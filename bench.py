@@ -76,6 +76,20 @@ def algorithmic_bytes(rows, dim, storage, batch, k):
     return rows * dim * ELEM[storage] + batch * dim * 4 + batch * k * 12
 
 
+def load_ncu_traffic(workload, path, world, rows):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            table = json.load(f)
+    except Exception:
+        return None
+    key = f"{workload}/{path}/{world}"
+    if rows != WORKLOADS[workload]["rows"]:
+        key = f"{workload}-shard-{rows}/{path}/{world}"
+    entry = table.get(key)
+    return entry["bytes"] if entry else None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -338,9 +352,12 @@ def run_b200(args, w):
             return base.search_device(q_dev, k, w["min_score"], out=res_out, defer_check=True)
         return sharded.search_tensors(q_dev, k, w["min_score"], defer_check=True)
 
+    fallbacks = [0]
+
     def finish_resident():
-        redone = base.finish_search() if sharded is None else sharded.finish()
-        assert redone == 0, f"{redone} queries took the exact fallback on synthetic data"
+        # exact fallbacks are legitimate (probability ~1e-7 per query) and their cost stays in the
+        # timed region; they are counted and reported
+        fallbacks[0] += base.finish_search() if sharded is None else sharded.finish()
 
     def step_e2e():
         # public host API: pinned host queries -> H2D -> search -> D2H of the hits
@@ -475,10 +492,12 @@ def run_b200(args, w):
                 "ms_per_step": e2e_ms_step, "wall_ms_per_step": wall_e2e * 1e3 / args.steps,
                 "api": "VectorBase.search_arrays(host float32 queries) -> host int64/float32 hits"},
         "gpu_launches": launches_per_step * args.steps,
+        "exact_fallback_queries": fallbacks[0],
         "roofline": {
             "bound": "hbm", "kernel": "scan_rows_kernel" if path == "scan" else "mma_topk_kernel (" + path + ")",
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "of": peaks["source"], "traffic": None, "kernel_ms_per_step": kernel_ms,
+            "of": peaks["source"], "traffic": load_ncu_traffic(args.workload, path, world, rows),
+            "kernel_ms_per_step": kernel_ms,
             "per_step_ms_by_kernel_kind": breakdown,
             "algorithmic_bytes_per_step": algo_bytes,
             "bytes_actually_requested_per_step": algo_launch_bytes,

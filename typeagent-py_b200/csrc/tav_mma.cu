@@ -739,15 +739,14 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
     p.n_tiles = static_cast<int>((n_rows + kBN - 1) / kBN);
     p.kb_count = (dim + kBK - 1) / kBK;
     p.reg_top = k <= kRegK;
-    // Rows we aim to admit per query.  The threshold is the m-th largest (m = kSampleTop) of a
-    // uniform sample of S = m*N/target rows, so about `target` rows of the corpus lie above it.
-    // Starvation (< k admitted) needs m of the corpus' top k inside the sample — expected k*m/target
-    // <= 1: probability <= 1e-5 per query; overflow (> 8*target) is rarer still.  Either way the query
-    // is merely redone by the exact row scan.
-    // 8k keeps starvation at ~1e-5 per query (Poisson(1) >= 8); small corpora aim lower (1/4096 of
-    // the rows, never below 512) so that admitted rows stay sparse in the MAIN epilogue.
+    // Rows we aim to admit per query (`target`).  The threshold is the m-th largest (m = kSampleTop = 8)
+    // of a uniform sample of S = m*N/target rows; the number of corpus rows above it, times S/N, is
+    // ~Gamma(m), so a query starves (< k admitted) with probability P(Gamma(8) < 8k/target): 6e-8 at
+    // target = 16k, but 1e-5 at 8k — one in a hundred thousand query-searches, which one 8-GPU benchmark
+    // run does hit.  Overflow (> 8*target admitted) is rarer still.  Either way the query is merely redone
+    // by the exact row scan.  Large corpora aim at 2048 rows; never fewer than 16k or 512.
     const int64_t target =
-        std::max<int64_t>(std::max<int64_t>(8ll * k, 512), std::min<int64_t>(2048, n_rows / 4096));
+        std::max<int64_t>(std::max<int64_t>(16ll * k, 512), std::min<int64_t>(2048, n_rows / 4096));
     if (n_rows <= 16384 || 8 * target >= n_rows) {
         p.n_sample = 0;
         p.capg = static_cast<uint32_t>(n_rows);
