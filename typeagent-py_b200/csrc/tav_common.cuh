@@ -95,6 +95,21 @@ __device__ __forceinline__ int list_push(CandList l, uint64_t key, int watermark
     return slot + 1 > watermark;
 }
 
+// Warp-aggregated push for kernels where a whole warp feeds ONE list (select / finalize / merge):
+// every lane calls it (convergently) with its own `want`; one shared-memory atomic per warp instead
+// of one per key.
+__device__ __forceinline__ int list_push_warp(CandList l, uint64_t key, bool want, int watermark) {
+    const unsigned lanes = __ballot_sync(0xFFFFFFFFu, want);
+    if (lanes == 0) return 0;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(lanes) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(l.count, __popc(lanes));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (want) l.keys[base + __popc(lanes & ((1u << lane) - 1u))] = key;
+    return base + __popc(lanes) > watermark;
+}
+
 inline int next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;

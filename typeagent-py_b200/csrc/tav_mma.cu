@@ -664,12 +664,13 @@ finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t capg,
             list_compact<kSelectThreads>(l, cap, k, 0);
         }
         const uint32_t i = base + tid;
+        uint64_t key = 0;
         if (i < total) {
             const uint64_t e = in[i];
             const float x = __uint_as_float(static_cast<uint32_t>(e >> 32));
-            const uint64_t key = make_key(score_from_dot(x), static_cast<uint32_t>(e));
-            if (key >= s_admit) need |= list_push(l, key, cap - kSelectThreads);
+            key = make_key(score_from_dot(x), static_cast<uint32_t>(e));
         }
+        need |= list_push_warp(l, key, i < total && key >= s_admit, cap - kSelectThreads);
     }
     __syncthreads();
     list_compact<kSelectThreads>(l, cap, k, 0);

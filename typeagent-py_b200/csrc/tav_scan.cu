@@ -313,10 +313,8 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(const SelectArgs
             list_compact<kSelectThreads>(l, cap, a.k, 0);
         }
         const uint32_t i = base + tid;
-        if (i < total) {
-            const uint64_t key = in[i];
-            if (key >= s_admit) need |= list_push(l, key, cap - kSelectThreads);
-        }
+        const uint64_t key = i < total ? in[i] : 0;
+        need |= list_push_warp(l, key, i < total && key >= s_admit, cap - kSelectThreads);
     }
     __syncthreads();
     list_compact<kSelectThreads>(l, cap, a.k, 0);  // final sort (also when total == 0)
@@ -377,14 +375,17 @@ merge_kernel(int n_lists, int n_queries, int k, const int64_t* items, const floa
             list_compact<kSelectThreads>(l, cap, k, 0);
         }
         const int64_t i = base + tid;
+        uint64_t key = 0;
+        bool want = false;
         if (i < total) {
             const int g = static_cast<int>(i / k), j = static_cast<int>(i % k);
             if (j < counts[g * counts_stride + q]) {
                 const float sc = scores[g * scores_stride + static_cast<size_t>(q) * k + j];
-                const uint64_t key = make_key(sc, static_cast<uint32_t>(g * k + (k - 1 - j)));
-                if (key >= s_admit) need |= list_push(l, key, cap - kSelectThreads);
+                key = make_key(sc, static_cast<uint32_t>(g * k + (k - 1 - j)));
+                want = key >= s_admit;
             }
         }
+        need |= list_push_warp(l, key, want, cap - kSelectThreads);
     }
     __syncthreads();
     list_compact<kSelectThreads>(l, cap, k, 0);
