@@ -33,7 +33,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     settings = tab.TextEmbeddingIndexSettings(O.FakeEmbeddingModel())
     for storage, n, d, b, k, ms in (("float32", 30011, 96, 7, 25, 0.45), ("bfloat16", 200003, 256, 200, 100, 0.0),
-                                    ("float16", 70001, 128, 33, 10, 0.5)):
+                                    ("float16", 70001, 128, 33, 10, 0.5), ("float32", 90001, 128, 40, 20, 0.0),
+                                    ("bfloat16", 120000, 64, 300, 5, 0.0)):
         v, q = O.make_corpus(n, d, seed=n, n_queries=b)
         vr, qr = O.round_to_storage(v, storage), O.round_to_storage(q, storage)
         sh = ShardedVectorBase(settings, device=local, storage_dtype=storage)
