@@ -72,6 +72,8 @@ for st in $stages; do
       timeout 600 python bench.py --rows 1250000 --steps 40 --warmup 5 --no-cpu-baseline 2>gpurun_out/bench_shard8.err | tee gpurun_out/bench_shard8.json
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:mma_topk -s 3 -c 1 \
         -o gpurun_out/prof_shard8 -f python bench.py --rows 1250000 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_shard8.log 2>&1 ;;
+    refbench)
+      timeout 600 python tools/benchmark_vectorbase_gpu.py --json gpurun_out/benchmark_vectorbase_gpu.json 2>&1 | tail -40 | tee gpurun_out/benchmark_vectorbase_gpu.log ;;
     latency)
       timeout 600 python tools/latency_probe.py 2>&1 | tail -8 | tee gpurun_out/latency_probe.log ;;
     hypo)

@@ -85,6 +85,7 @@ struct PinBuf {
 
 constexpr int kMaxTimedChunks = 64;
 constexpr size_t kPinnedStageLimit = size_t(8) << 20;  // payloads above this go straight from user memory
+constexpr size_t kZeroCopyOutLimit = size_t(16) << 10; // results up to this size are written to host memory by the kernels
 
 }  // namespace tav
 
@@ -586,7 +587,16 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
     const size_t off_scores = nk * sizeof(int64_t);
     const size_t off_counts = off_scores + ((nk * sizeof(float) + 7) & ~size_t(7));
     const size_t pack_bytes = off_counts + ((static_cast<size_t>(n_queries) * sizeof(int32_t) + 7) & ~size_t(7));
-    if (!o_dev) {
+    // Small result sets are written by the kernels straight into the pinned host staging (zero
+    // copy over PCIe: no D2H memcpy call on the single-lookup latency path).
+    const bool zero_copy_out = !o_dev && pack_bytes <= kZeroCopyOutLimit;
+    if (zero_copy_out) {
+        TAV_CUDA(ix->pin_out.ensure(pack_bytes));
+        char* base = static_cast<char*>(ix->pin_out.p);
+        d_items = reinterpret_cast<int64_t*>(base);
+        d_scores = reinterpret_cast<float*>(base + off_scores);
+        d_counts = reinterpret_cast<int32_t*>(base + off_counts);
+    } else if (!o_dev) {
         TAV_CUDA(ix->out_pack.ensure(pack_bytes));
         char* base = static_cast<char*>(ix->out_pack.p);
         d_items = reinterpret_cast<int64_t*>(base);
@@ -602,11 +612,8 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
 
     if (n_scan == 0 || ix->size == 0 || ix->dim == 0) {
         // empty corpus / empty subset: no hits (vectorbase.py:174-175, :214-215)
-        TAV_CUDA(cudaMemsetAsync(d_counts, 0, static_cast<size_t>(n_queries) * sizeof(int32_t), s));
-        if (!o_dev) {
-            memset(out_counts, 0, static_cast<size_t>(n_queries) * sizeof(int32_t));
-            TAV_CUDA(cudaStreamSynchronize(s));
-        }
+        if (o_dev) TAV_CUDA(cudaMemsetAsync(d_counts, 0, static_cast<size_t>(n_queries) * sizeof(int32_t), s));
+        else memset(out_counts, 0, static_cast<size_t>(n_queries) * sizeof(int32_t));
         return TAV_OK;
     }
     if (n_scan > 0xFFFFFFFFll) {
@@ -759,7 +766,13 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
     if (ix->timing_on) TAV_CUDA(cudaEventRecord(ix->ev_total[1], s));
     ix->timing_valid = true;
 
-    if (!o_dev) {
+    if (zero_copy_out) {
+        TAV_CUDA(cudaStreamSynchronize(s));
+        const char* h = static_cast<const char*>(ix->pin_out.p);
+        memcpy(out_items, h, nk * sizeof(int64_t));
+        memcpy(out_scores, h + off_scores, nk * sizeof(float));
+        memcpy(out_counts, h + off_counts, static_cast<size_t>(n_queries) * sizeof(int32_t));
+    } else if (!o_dev) {
         if (pack_bytes <= kPinnedStageLimit) {
             TAV_CUDA(ix->pin_out.ensure(pack_bytes));
             TAV_CUDA(cudaMemcpyAsync(ix->pin_out.p, ix->out_pack.p, pack_bytes, cudaMemcpyDeviceToHost, s));

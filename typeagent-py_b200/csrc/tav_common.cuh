@@ -110,6 +110,19 @@ __device__ __forceinline__ int list_push_warp(CandList l, uint64_t key, bool wan
     return base + __popc(lanes) > watermark;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs a driver call; remember, per device, the
+// largest size already granted to a kernel and only call again to raise it.
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kern, size_t bytes, int (&granted)[16]) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 16 && static_cast<size_t>(granted[dev]) >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (e == cudaSuccess && dev >= 0 && dev < 16) granted[dev] = static_cast<int>(bytes);
+    return e;
+}
+
 inline int next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;

@@ -789,8 +789,8 @@ struct Maps {
 template <int MODE, int CG, bool SPLIT>
 cudaError_t launch_kernel_cg(const Maps& m, const KernelArgs& ka, uint32_t idesc, int units, cudaStream_t s) {
     auto kern = mma_topk_kernel<MODE, CG, SPLIT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(kSmemBytes));
+    static int granted[16] = {};
+    cudaError_t e = ensure_dynamic_smem(kern, kSmemBytes, granted);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(units * CG));
@@ -982,8 +982,8 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
         ++n_launch;
 
         const size_t sel_smem = static_cast<size_t>(next_pow2(a.k + kSelectThreads)) * sizeof(uint64_t);
-        e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(sel_smem));
+        static int finalize_granted[16] = {};
+        e = ensure_dynamic_smem(finalize_kernel, sel_smem, finalize_granted);
         if (e != cudaSuccess) return e;
         if ((e = ev_begin()) != cudaSuccess) return e;
         finalize_kernel<<<nq, kSelectThreads, sel_smem, s>>>(

@@ -265,8 +265,8 @@ static cudaError_t launch_scan_t(const ScanArgs& a, cudaStream_t s) {
     const bool vec = (row_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(a.corpus) % 16 == 0);
     const size_t smem = scan_smem_bytes(QB, a.dim, a.k);
     auto kern = vec ? scan_rows_kernel<T, QB, true> : scan_rows_kernel<T, QB, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+    static int granted[2][16] = {};
+    cudaError_t e = ensure_dynamic_smem(kern, smem, granted[vec ? 1 : 0]);
     if (e != cudaSuccess) return e;
     kern<<<a.grid, kScanThreads, smem, s>>>(a);
     return cudaGetLastError();
@@ -342,8 +342,8 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(const SelectArgs
 
 cudaError_t launch_select(const SelectArgs& a, cudaStream_t s) {
     const size_t smem = static_cast<size_t>(select_cap(a.k)) * sizeof(uint64_t);
-    cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+    static int granted[16] = {};
+    cudaError_t e = ensure_dynamic_smem(select_kernel, smem, granted);
     if (e != cudaSuccess) return e;
     select_kernel<<<a.nq, kSelectThreads, smem, s>>>(a);
     return cudaGetLastError();
@@ -413,8 +413,8 @@ cudaError_t launch_merge(int n_lists, int n_queries, int k, const int64_t* items
     if (scores_stride == 0) scores_stride = static_cast<int64_t>(n_queries) * k;
     if (counts_stride == 0) counts_stride = n_queries;
     const size_t smem = static_cast<size_t>(select_cap(k)) * sizeof(uint64_t);
-    cudaError_t e = cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+    static int granted[16] = {};
+    cudaError_t e = ensure_dynamic_smem(merge_kernel, smem, granted);
     if (e != cudaSuccess) return e;
     merge_kernel<<<n_queries, kSelectThreads, smem, s>>>(n_lists, n_queries, k, items, scores,
                                                          counts, items_stride, scores_stride,

@@ -122,6 +122,7 @@ class VectorBase:
         self._ix_rows = 0
         self._device_only_rows = 0  # rows living only on the device (from_device_tensor)
         self._adopted_tensor = None
+        self._single_out: dict[int, tuple] = {}  # k -> reusable result arrays of fuzzy_lookup_embedding
         self.force_path: str | None = None  # "scan" | "mma" | None (tests / benchmarks)
         self._timing = False
         self.clear()
@@ -427,9 +428,18 @@ class VectorBase:
         k = self._resolve_k(max_hits, n)
         if predicate is not None:
             return self._lookup_with_predicate(embedding, k, min_score, predicate)
-        items, scores, counts = self.search_arrays(embedding, k, min_score)
+        # single-lookup latency path: result buffers are reused across calls (they never escape:
+        # the hits are copied into ScoredInt objects right here)
+        k_eff = max(1, min(k, n))
+        out = self._single_out.get(k_eff)
+        if out is None:
+            if len(self._single_out) > 8:
+                self._single_out.clear()
+            out = self._single_out[k_eff] = (np.empty((1, k_eff), np.int64), np.empty((1, k_eff), np.float32),
+                                             np.empty(1, np.int32))
+        items, scores, counts = self.search_arrays(embedding, k, min_score, out=out)
         c = int(counts[0])
-        return [ScoredInt(int(i), float(s)) for i, s in zip(items[0, :c], scores[0, :c])]
+        return [ScoredInt(i, s) for i, s in zip(items[0, :c].tolist(), scores[0, :c].tolist())]
 
     def _lookup_with_predicate(self, embedding, k, min_score, predicate) -> list[ScoredInt]:
         """Reference semantics (vectorbase.py:191-201): every row at or above min_score that
