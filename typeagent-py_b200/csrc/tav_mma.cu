@@ -7,30 +7,35 @@
 // values are exact in float32, so on storage-rounded inputs only the summation order differs
 // from the reference's sgemv.
 //
-// Shape of one CTA (persistent, one per SM, 320 threads):
+// Shape of one CTA (persistent, one per SM, 320 threads; see the template comment below for the
+// CTA-pair and split-precision forms):
 //   warp 0     TMA producer: per (corpus tile, query block, 64-wide K slice) loads the query
-//              slice [128 x 64] and the corpus slice [256 x 64] into a 4-stage smem ring
-//              (128-byte swizzle), completing on an mbarrier.
-//   warp 1     MMA issuer: one elected thread issues tcgen05.mma.kind::f16 M=128 N=256 K=16
-//              (4 per stage), accumulating into one of two 256-column TMEM stages;
-//              tcgen05.commit frees the smem slot / publishes the accumulator.
+//              slice [128 x 64] and this CTA's corpus slice ([128 x 64] in a pair, [256 x 64]
+//              alone) into a smem ring (6 x 32 KB / 4 x 48 KB, 128-byte swizzle), completing on
+//              an mbarrier.
+//   warp 1     MMA issuer: one elected thread (of the pair's leader CTA) issues tcgen05.mma
+//              .kind::f16 M=256 (pair) or 128, N=256, K=16 — 4 per stage — into one of two
+//              256-column TMEM accumulator stages; tcgen05.commit frees the smem slot (in both
+//              CTAs) and publishes the accumulator.
 //   warps 2-9  epilogue: tcgen05.ld 32 lanes x 32 columns, double-buffered in registers — a
 //              thread owns ONE query (its TMEM lane) and half of the tile's 256 rows.  Per
 //              32-row chunk it takes the max of the 32 dots (branch-free) and compares it with
 //              the query's admission threshold; only chunks that contain an admitted row take
-//              the slow path that appends (dot, row) pairs to the query's global candidate
-//              buffer.  Runs concurrently with the next tile's MMAs (two TMEM stages).
+//              the slow path (branch-free mask, one atomicAdd per lane, predicated stores of
+//              (dot, row) pairs into the query's global candidate buffer).  Runs concurrently
+//              with the next tile's MMAs (two TMEM stages).
 //
-// Admission thresholds.  A first launch of the same kernel in SAMPLE mode scores a strided
-// sample of corpus tiles and keeps, per query, the 16 largest dots in registers; a tiny kernel
-// turns the 16th largest into a threshold (lowered to the bottom of its float32 score class and
-// never below the caller's min_score) expected to admit ~2k..16k rows of the full corpus.  The
-// MAIN launch then streams the whole corpus once; a finalize kernel maps the admitted dots to
-// scores and selects the top k with the library's total order.  Exactness: every row not
-// admitted scores strictly below every admitted row, so if at least k rows were admitted (or the
-// threshold is the caller's min_score itself) the result is the exact top-k.  Queries for which
-// neither holds (pathological score distributions) or whose buffer overflowed are flagged and
-// redone by the exact row-scan path.
+// Admission thresholds (k > 8).  A first launch of the same kernel in SAMPLE mode scores a strided
+// sample of corpus tiles and keeps, per thread, its 8 largest dots in registers; a warp-per-query
+// k-way merge takes the 8th largest overall and turns it into a threshold (lowered to the bottom of
+// its float32 score class and never below the caller's min_score) expected to admit max(16k, 512)
+// to 2048 rows of the corpus.  The MAIN launch then streams the whole corpus once; a finalize
+// kernel maps the admitted dots to scores and selects the top k with the library's total order.
+// Exactness: every row not admitted scores strictly below every admitted row, so if at least k
+// rows were admitted (or the threshold is the caller's min_score itself) the result is the exact
+// top-k.  Queries for which neither holds (pathological score distributions; probability ~6e-8 on
+// well-mixed data) or whose buffer overflowed are flagged and redone by the exact row-scan path.
+// For k <= 8 (REGTOP mode) there is no sampling: the top k live in registers for the whole scan.
 //
 // Algorithmic bytes per search: N*D*2 (corpus, read once per <=256 queries) + queries + hits.
 
