@@ -65,6 +65,9 @@ for st in $stages; do
         -k "search_matches_oracle or in_register or fallback" 2>&1 | tail -25 | tee gpurun_out/sanitizer_mma.log
       timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
         -k "batched_equals or multi_pass" 2>&1 | tail -15 | tee gpurun_out/sanitizer_race.log ;;
+    bench_g8only)
+      timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 \
+        bench.py --gpus 8 --steps 40 --warmup 5 2>gpurun_out/bench_g8.err | tee gpurun_out/bench_g8.json ;;
     bench_c4_g8)
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 \
         bench.py --gpus 8 --workload c4 --steps 20 --warmup 3 2>gpurun_out/bench_c4_g8.err | tee gpurun_out/bench_c4_g8.json ;;
