@@ -104,6 +104,26 @@ def test_in_register_topk_ties_and_duplicates():
         assert [h.item for h in hits] == list(range(19999, 19992, -1))
 
 
+@pytest.mark.parametrize("storage,k", [("bfloat16", 20), ("bfloat16", 4), ("float32", 20)])
+def test_thresholds_on_the_tensor_core_path(storage, k):
+    """min_score edges through the admission-threshold machinery: nothing can pass (> 1), everything
+    passes (negative), and a threshold equal to an achieved score keeps that row (>=)."""
+    v, q = O.make_corpus(20000, 64, seed=77, n_queries=24)
+    if storage != "float32":
+        v, q = O.round_to_storage(v, storage), O.round_to_storage(q, storage)
+    base = make_base(v, storage, None)
+    assert all(h == [] for h in base.fuzzy_lookup_embeddings(q, k, 1.5))
+    assert base.last_timing()["path"] in ("mma", "mma_split")
+    everything = base.fuzzy_lookup_embeddings(q, k, -2.0)
+    top = base.fuzzy_lookup_embeddings(q, k, 0.0)
+    assert [[h.item for h in a] for a in everything] == [[h.item for h in b] for b in top]
+    cut = float(top[5][k // 2].score)
+    again = base.fuzzy_lookup_embeddings(q, k, cut)[5]
+    assert [h.item for h in again] == [h.item for h in top[5][: k // 2 + 1]]
+    for i in (0, 5, 23):
+        assert_hits_match(base.fuzzy_lookup_embeddings(q, k, 0.55)[i], O.lookup(v, q[i], k, 0.55), min_score=0.55)
+
+
 def test_unrounded_float32_queries_are_rounded_like_the_corpus():
     v, q = O.make_corpus(20000, 256, seed=5, n_queries=20)
     base = make_base(v, "bfloat16")
