@@ -7,15 +7,26 @@ the whole corpus is scored against B queries and the k best rows per query are r
 Default workload (BASELINE.json `metric`: "top-k cosine on 10M x 768"): configs[2] =
 10M x 768 bf16 corpus, batch 256, top-100, on one B200.  With --gpus N (launched by
 torch.distributed.run, one rank per GPU) the SAME corpus is row-sharded over the N GPUs
-(strong scaling): every rank searches its rows, per-rank candidates are exchanged with one
-NCCL all-gather and merged on every rank.
+(strong scaling): every rank searches its rows, per-rank candidates are exchanged and merged on
+every rank.
 
-Output: ONE JSON line (rank 0).  `value` = queries/sec with inputs resident in HBM, timed
-with CUDA events over exactly --steps steps (max over ranks); `e2e` = the same through the
-public host API (pinned host queries -> H2D -> search -> D2H results) inside the timed
-region; `roofline` = the dominant kernel's algorithmic bytes / its event-timed duration
-against MEASURED_PEAKS.json; `cpu_baseline` = the reference algorithm (oracle port, numpy)
-on this box's host cores on a bounded sample.  `--impl reference` times that CPU path alone.
+Output: ONE JSON line (rank 0).
+  value      queries/sec with inputs resident in HBM, CUDA events over exactly --steps steps
+             (max over ranks);
+  e2e        the same through the public host API (pinned host queries -> H2D -> search -> D2H
+             results) inside the timed region;
+  roofline   the dominant kernel's algorithmic bytes / its event-timed duration — events recorded
+             by libtavec around that kernel INSIDE the timed region of `value` (same pass, so
+             kernel_ms_per_step <= ms_per_step by construction) — against MEASURED_PEAKS.json;
+             `sustained` repeats it over >= 2 s of back-to-back steps (the power-capped figure);
+  cpu_baseline  the reference's own VectorBase (unmodified file, vendored under oracle/_ref by
+             build(); else the numpy restatement) on this box's host cores over the FULL corpus;
+  parity_checked  4 queries of the final step compared with the blocked numpy oracle over the
+             device corpus at the contract tolerances;
+  secondary  the other single-GPU BASELINE configs (c1, c2, c5; c4 at 8 GPUs), each with its own
+             value / e2e / roofline / cpu_baseline.
+`--impl reference` times the reference's CPU path alone (same metric / config strings, so the
+driver can divide).
 """
 
 from __future__ import annotations
@@ -50,8 +61,13 @@ WORKLOADS = {
                   desc="RelatedTerms 50k x 384 float32 (as the reference stores it), 1000 query terms, top-5"),
     "c2f32": dict(rows=1_000_000, dim=768, storage="float32", batch=64, k=32, min_score=0.0,
                   desc="1M x 768 float32, batch 64, top-32 (split-precision tensor path)"),
+    "s1": dict(rows=10_000_000, dim=768, storage="float32", batch=1, k=10, min_score=0.0,
+               desc="10M x 768 fp32, 1 query, top-10 (row-scan path at scale)"),
+    "s8": dict(rows=10_000_000, dim=768, storage="float32", batch=8, k=10, min_score=0.0,
+               desc="10M x 768 fp32, 8 queries, top-10 (row-scan path at scale)"),
 }
 ELEM = {"float32": 4, "bfloat16": 2, "float16": 2}
+SEED = 20260922
 
 
 def parse_args():
@@ -61,14 +77,22 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", choices=["b200", "reference"], default="b200")
     p.add_argument("--workload", choices=sorted(WORKLOADS), default="c3")
-    p.add_argument("--rows", type=int, default=None, help="override corpus rows (experiments)")
+    p.add_argument("--rows", type=int, default=None, help="override corpus rows (experiments / tests)")
     p.add_argument("--batch", type=int, default=None)
     p.add_argument("--k", type=int, default=None)
     p.add_argument("--path", choices=["auto", "scan", "mma"], default="auto")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--cpu-sample-rows", type=int, default=400_000)
-    p.add_argument("--cpu-sample-queries", type=int, default=16)
+    p.add_argument("--no-secondary", action="store_true", help="skip the c1/c2/c5 (c4 at 8 GPUs) block")
+    p.add_argument("--no-parity", action="store_true", help="skip the blocked-oracle check of the final step")
+    p.add_argument("--sustain-seconds", type=float, default=2.0, help="0 disables the sustained roofline run")
+    p.add_argument("--cpu-queries", type=int, default=8, help="timed single-query lookups of the cpu_baseline leg")
     return p.parse_args()
+
+
+def metric_string(w):
+    """The SAME string for the repo arm and the reference arm (the driver divides like by like)."""
+    return ("queries/sec, top-k cosine (VectorBase.fuzzy_lookup_embedding) on "
+            f"{w['rows']}x{w['dim']} {w['storage']}, batch {w['batch']}, top-{w['k']}")
 
 
 def algorithmic_bytes(rows, dim, storage, batch, k):
@@ -100,94 +124,160 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def workload_config(w, n_gpus):
+    return {
+        "workload": w["desc"], "rows": w["rows"], "dim": w["dim"], "storage": w["storage"],
+        "batch": w["batch"], "k": w["k"], "min_score": w["min_score"],
+        "parallelism": f"row-sharded x{n_gpus}, candidate exchange + merge on every rank" if n_gpus > 1 else "single GPU",
+        "l2": "corpus shard >> 126 MB L2, no flush needed" if w["rows"] * w["dim"] * ELEM[w["storage"]] / n_gpus > 4e8
+              else "corpus fits L2: L2 flushed (256 MB write) between timed steps",
+    }
+
+
 # ----------------------------------------------------------------------------- CPU side
-def cpu_reference_leg(w, sample_rows, sample_queries, repeats=1):
-    """The reference's algorithm on host cores: one VectorBase lookup per query
-    (np.dot sgemv -> score -> threshold -> argpartition), as every caller of the reference
-    does (storage/memory/reltermsindex.py:326-331), on a bounded sample of the workload:
-    `sample_rows` rows of the corpus (float32, as the reference stores them) x
-    `sample_queries` queries.  Full-corpus q/s is extrapolated linearly in rows (the lookup
-    is a streaming O(N*D) scan)."""
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def set_blas_threads(n):
+    """Pin the BLAS pool to `n` threads whatever OMP_NUM_THREADS says (torch.distributed.run exports
+    OMP_NUM_THREADS=1); returns (context manager or None, threads the pool reports)."""
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        ctl = threadpool_limits(limits=n, user_api="blas")
+        got = [i.get("num_threads") for i in threadpool_info() if i.get("user_api") == "blas"]
+        return ctl, (max(got) if got else n)
+    except Exception:
+        return None, n
+
+
+def make_host_corpus(rows, dim, seed, threads):
+    """Unit-norm float32 rows [rows, dim] on the host (what the reference stores), generated in
+    1M-row blocks on a thread pool (numpy generators release the GIL): block b uses seed + b, as
+    tools/benchmark_vectorbase.py:80-94 does for its single block."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    out = np.empty((rows, dim), dtype=np.float32)
+    block = 250_000
+
+    def fill(b):
+        lo, hi = b * block, min(rows, (b + 1) * block)
+        rng = np.random.default_rng(seed + b)
+        rng.standard_normal(out=out[lo:hi], dtype=np.float32)
+        out[lo:hi] /= np.linalg.norm(out[lo:hi], axis=1, keepdims=True)
+
+    n_blocks = -(-rows // block)
+    with ThreadPoolExecutor(max_workers=max(1, min(threads, n_blocks))) as ex:
+        list(ex.map(fill, range(n_blocks)))
+    return out
+
+
+class _NullModel:
+    model_name = "bench-null"
+
+    def add_embedding(self, key, embedding):
+        return None
+
+
+def make_cpu_lookup(vectors):
+    """(callable(query, k, min_score) -> hits, kind): the UNMODIFIED reference VectorBase when its
+    file is available (mounted, or vendored under oracle/_ref by build()), else the oracle port."""
+    from oracle import ref_loader
+
+    if ref_loader.reference_available():
+        vb, _ = ref_loader.load_reference()
+        base = vb.VectorBase(vb.TextEmbeddingIndexSettings(embedding_model=_NullModel()))
+        base.deserialize(vectors)  # adopts the array, no copy (vectorbase.py:273-287)
+        return (lambda q, k, ms: base.fuzzy_lookup_embedding(q, max_hits=k, min_score=ms)), "reference"
     from oracle import vectorbase_oracle as O
 
-    rows = min(sample_rows, w["rows"])
-    rng = np.random.default_rng(1234)
-    v = rng.standard_normal((rows, w["dim"]), dtype=np.float32)
-    v /= np.linalg.norm(v, axis=1, keepdims=True)
-    q = rng.standard_normal((sample_queries, w["dim"]), dtype=np.float32)
-    q /= np.linalg.norm(q, axis=1, keepdims=True)
-    O.lookup(v, q[0], w["k"], w["min_score"])  # warm-up (thread pool, page faults)
-    times = []
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        for qq in q:
-            O.lookup(v, qq, w["k"], w["min_score"])
-        times.append(time.perf_counter() - t0)
-    dt = min(times)
-    all_times = list(times)
-    # "strong" CPU baseline (SURVEY.md §8d-ii), for fairness: ONE sgemm for all sample queries, then the
-    # per-row ranking — what a batched numpy caller could do; the reference itself never batches.
-    t0 = time.perf_counter()
-    O.lookup_batch(v, q, w["k"], w["min_score"], one_gemm=True)
-    dt_gemm = time.perf_counter() - t0
-    qps_sample = sample_queries / dt
-    qps_full = qps_sample * rows / w["rows"]
-    threads = os.cpu_count()
-    try:
-        from threadpoolctl import threadpool_info
+    return (lambda q, k, ms: O.lookup(vectors, q, k, ms)), "port"
 
-        blas = [i for i in threadpool_info() if i.get("user_api") == "blas"]
-        if blas:
-            threads = blas[0].get("num_threads", threads)
-    except Exception:
-        pass
+
+def cpu_reference_leg(w, warmup, timed, want_batched=False):
+    """The reference's CPU path on this box's host cores, FULL workload rows (no extrapolation):
+    one VectorBase.fuzzy_lookup_embedding per query — np.dot sgemv over the whole float32 corpus ->
+    score -> threshold -> argpartition — as every caller of the reference does
+    (storage/memory/reltermsindex.py:326-331).  `warmup` + `timed` single-query lookups; the BLAS pool
+    is set to the cores this process may run on.  Returns per-query seconds (list) and metadata."""
+    threads = host_threads()
+    ctl, blas_threads = set_blas_threads(threads)
+    try:
+        t0 = time.perf_counter()
+        vectors = make_host_corpus(w["rows"], w["dim"], SEED + 1000, threads)
+        gen_s = time.perf_counter() - t0
+        rng = np.random.default_rng(7)
+        n_q = warmup + timed
+        q = rng.standard_normal((max(n_q, 1), w["dim"])).astype(np.float32)
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+        lookup, kind = make_cpu_lookup(vectors)
+        times = []
+        for i in range(n_q):
+            t0 = time.perf_counter()
+            hits = lookup(q[i], w["k"], w["min_score"])
+            times.append(time.perf_counter() - t0)
+            assert len(hits) == min(w["k"], w["rows"])
+        batched = None
+        if want_batched:
+            # "strong" CPU baseline (SURVEY.md §8d-ii): ONE sgemm for a few queries, then the per-row
+            # ranking — what a batched numpy caller could do; the reference itself never batches.
+            from oracle import vectorbase_oracle as O
+
+            nb = min(8, w["batch"])
+            t0 = time.perf_counter()
+            O.lookup_batch(vectors, q[:nb] if len(q) >= nb else np.repeat(q[:1], nb, 0), w["k"], w["min_score"],
+                           one_gemm=True)
+            batched = nb / (time.perf_counter() - t0)
+    finally:
+        if ctl is not None:
+            ctl.restore_original_limits()
+    steady = times[warmup:]
+    med = statistics.median(steady)
     return {
-        "value": qps_full,
-        "unit": "queries/s",
-        "cores": threads,
-        "kind": "port",
-        "sample": f"{rows} of {w['rows']} rows x {w['dim']} float32, {sample_queries} queries one lookup each "
-                  f"(numpy {np.__version__}), {dt:.3f} s; q/s scaled by rows ratio",
-        "sample_seconds": dt,
-        "all_seconds": all_times,
-        "batched_sgemm_value": sample_queries / dt_gemm * rows / w["rows"],
-        "sample_gbs": rows * w["dim"] * 4 * sample_queries / dt / 1e9,
+        "per_query_s": steady, "median_s": med, "kind": kind, "cores": blas_threads,
+        "gen_s": gen_s, "batched_sgemm_value": batched,
+        "sample": (f"FULL corpus {w['rows']} x {w['dim']} float32 ({w['rows'] * w['dim'] * 4 / 1e9:.1f} GB) resident on "
+                   f"the host; {timed} timed single-query lookups after {warmup} warm-up, median "
+                   f"{med * 1e3:.2f} ms/query; {blas_threads} BLAS threads of {threads} usable cores; "
+                   f"numpy {np.__version__}; " + ("unmodified reference VectorBase" if kind == "reference"
+                                                 else "numpy restatement (oracle/)")),
+        "gbs": w["rows"] * w["dim"] * 4 / med / 1e9,
     }
+
+
+def cpu_baseline_block(leg):
+    out = {"value": 1.0 / leg["median_s"], "unit": "queries/s", "cores": leg["cores"], "kind": leg["kind"],
+           "sample": leg["sample"], "host_gb_per_s": leg["gbs"]}
+    if leg.get("batched_sgemm_value"):
+        out["batched_sgemm_value"] = leg["batched_sgemm_value"]
+    return out
 
 
 def run_reference_impl(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # one step = one pass of the sample queries over the sample rows; corpus generated once
-    last = cpu_reference_leg(w, args.cpu_sample_rows, args.cpu_sample_queries,
-                             repeats=args.warmup + args.steps)
-    times = last["all_seconds"][args.warmup:]
-    dt = statistics.fmean(times)
-    rows = min(args.cpu_sample_rows, w["rows"])
-    qps = args.cpu_sample_queries / dt * rows / w["rows"]
-    last["value"] = qps
+    # one step = ONE single-query lookup over the full corpus (a bounded sample of the batch's B
+    # queries: the reference serves a batch as B such lookups); ms_per_step = B x median per query
+    leg = cpu_reference_leg(w, warmup=args.warmup, timed=args.steps)
+    qps = 1.0 / leg["median_s"]
     out = {
         "impl": "reference",
-        "metric": "queries/sec, top-k cosine (VectorBase.fuzzy_lookup_embedding), CPU reference path",
+        "metric": metric_string(w),
         "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, w, args.gpus),
-        "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "ms_per_step": w["batch"] * leg["median_s"] * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (unit-norm gaussian rows; seeds in bench.py)",
+        "config": workload_config(w, args.gpus),
+        "cpu_baseline": cpu_baseline_block(leg),
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "step_definition": "one step = one single-query lookup over the full corpus; ms_per_step = batch x "
+                           "median per-query time (the reference runs a batch as B sequential lookups)",
     }
     print(json.dumps(out), file=_RESULT_OUT, flush=True)
-
-
-def workload_config(args, w, n_gpus):
-    return {
-        "workload": w["desc"], "rows": w["rows"], "dim": w["dim"], "storage": w["storage"],
-        "batch": w["batch"], "k": w["k"], "min_score": w["min_score"],
-        "parallelism": f"row-sharded x{n_gpus}, candidate all-gather" if n_gpus > 1 else "single GPU",
-        "l2": "corpus shard >> 126 MB L2, no flush needed" if w["rows"] * w["dim"] * ELEM[w["storage"]] / n_gpus > 4e8
-              else "corpus fits L2: L2 flushed (256 MB write) between timed steps",
-    }
 
 
 # ----------------------------------------------------------------------------- GPU side
@@ -251,16 +341,18 @@ class ClockSampler:
             except Exception:
                 pass
 
-    def stop(self):
-        self._stop.set()
-        self.thread.join(timeout=5)
+    def mark(self):
+        return len(self.samples)
+
+    def summary(self, first=0):
         # NVML clocks-event reason bits
         names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                  0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
-        sm = [s for s, _, _ in self.samples]
-        pw = [p for _, p, _ in self.samples]
+        part = self.samples[first:]
+        sm = [s for s, _, _ in part]
+        pw = [p for _, p, _ in part]
         mask = 0
-        for _, _, r in self.samples:
+        for _, _, r in part:
             mask |= r
         reasons = sorted(n for bit, n in names.items() if mask & bit)
         # "under load": samples whose power is within 25% of the run's maximum
@@ -269,6 +361,11 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_min_mhz": min(busy) if busy else None,
                 "sm_max_mhz": self.sm_max, "power_w_max": pmax if pw else None, "samples": len(sm),
                 "source": self.source, "reasons": reasons}
+
+    def stop(self):
+        self._stop.set()
+        self.thread.join(timeout=5)
+        return self.summary()
 
 
 def make_shard_on_device(torch, device, lo, hi, dim, storage, seed):
@@ -294,43 +391,64 @@ def make_shard_on_device(torch, device, lo, hi, dim, storage, seed):
     return out
 
 
-def run_b200(args, w):
-    import torch
-    import torch.distributed as dist
+class Bench:
+    """Device-side state shared by the workloads of one run."""
 
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.device)
+        self.peaks = load_peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.world == 1:
+            return ms
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def measure(bn: Bench, name, w, steps, warmup, *, force=None, sustain_s=0.0, parity=True, cpu=True, cpu_queries=8):
+    """One workload on the GPUs of this run -> the result dict (rank 0) or None (other ranks)."""
     import typeagent_py_b200 as tab
     from typeagent_py_b200.sharded import ShardedVectorBase, shard_bounds
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
-
+    torch, world, rank, device = bn.torch, bn.world, bn.rank, bn.device
     rows, dim, storage, batch, k = w["rows"], w["dim"], w["storage"], w["batch"], w["k"]
     lo, hi = shard_bounds(rows, world)[rank]
-    corpus = make_shard_on_device(torch, device, lo, hi, dim, storage, seed=20260922)
+    corpus = make_shard_on_device(torch, device, lo, hi, dim, storage, seed=SEED)
     torch.cuda.synchronize()
 
     settings = tab.TextEmbeddingIndexSettings(embedding_model=_NullModel(), min_score=w["min_score"])
-    force = None if args.path == "auto" else args.path
     if world == 1:
         base = tab.VectorBase.from_device_tensor(settings, corpus)
-        base.force_path = force
         sharded = None
     else:
-        sharded = ShardedVectorBase(settings, device=local_rank, storage_dtype=storage)
+        sharded = ShardedVectorBase(settings, device=bn.local_rank, storage_dtype=storage)
         sharded.load_local_shard(corpus, rows)
         base = sharded._engine.base
-        base.force_path = force
-
-    base.enable_timing()  # events around the kernels: needed for the roofline block
+    base.force_path = force
+    base.enable_timing()  # events around the kernels, recorded inside the timed region
 
     rng = np.random.default_rng(7)
     q_host = torch.empty((batch, dim), dtype=torch.float32).pin_memory()
@@ -343,17 +461,14 @@ def run_b200(args, w):
     out_counts = torch.empty((batch,), dtype=torch.int32).pin_memory()
 
     shard_bytes = (hi - lo) * dim * ELEM[storage]
-    flush = None
-    if shard_bytes < 4e8:
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device) if shard_bytes < 4e8 else None
     res_out = (torch.empty((batch, k), dtype=torch.int64, device=device),
                torch.empty((batch, k), dtype=torch.float32, device=device),
                torch.empty((batch,), dtype=torch.int32, device=device))
 
     def step_resident():
         # fully asynchronous; the "did any query need the exact fallback" check of every step is
-        # accumulated on the device and resolved by finish_resident() inside the timed region
+        # kept on the device and resolved by finish_resident() inside the timed region
         if sharded is None:
             return base.search_device(q_dev, k, w["min_score"], out=res_out, defer_check=True)
         return sharded.search_tensors(q_dev, k, w["min_score"], defer_check=True)
@@ -378,62 +493,66 @@ def run_b200(args, w):
         torch.cuda.current_stream().synchronize()
         return out_items, out_scores, out_counts
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def history(n):
+        """per-kernel times of the last n searches (events recorded by libtavec inside the region)"""
+        import ctypes as C
 
-    def timed(fn, steps, per_step_sync):
-        """Time exactly `steps` steps with CUDA events; returns total ms (this rank)."""
+        from typeagent_py_b200 import _capi
+
+        cap = 64
+        arr = [(C.c_float * cap)() for _ in range(4)]
+        got = C.c_int(0)
+        _capi.check(_capi.load().tav_timing_history(base._ix, min(cap, n), arr[0], arr[1], arr[2], arr[3], C.byref(got)))
+        m = got.value
+        return {"main": list(arr[0][:m]), "sample": list(arr[1][:m]), "aux": list(arr[2][:m]), "search_total": list(arr[3][:m])}
+
+    def timed_resident(n_steps):
+        """EXACTLY n_steps steps, CUDA events on the launching stream; returns total ms (this rank)."""
         total = 0.0
-        if flush is None and not per_step_sync:
-            barrier()
+        if flush is None:
+            bn.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(steps):
-                fn()
+            for i in range(n_steps):
+                step_resident()
+                if (i & 31) == 31:
+                    finish_resident()      # at most 64 searches may be outstanding
             finish_resident()
             e1.record()
-            barrier()
+            bn.barrier()
             return e0.elapsed_time(e1)
-        for _ in range(steps):
-            if flush is not None:
-                flush.fill_(1)
-            barrier()
+        for _ in range(n_steps):
+            flush.fill_(1)
+            bn.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fn()
+            step_resident()
             finish_resident()
             e1.record()
-            barrier()
+            bn.barrier()
             total += e0.elapsed_time(e1)
         return total
 
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     # warm-up (both legs), then the timed regions
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_resident()
         finish_resident()
         step_e2e()
-    barrier()
+    bn.barrier()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms_resident = max_over_ranks(timed(step_resident, args.steps, per_step_sync=False))
-    launches_per_step = base.last_timing()["launches"] + (1 if world > 1 else 0)
-    path = base.last_timing()["path"]
+    sampler = ClockSampler(bn.local_rank) if rank == 0 else None
+    ms_resident = bn.max_over_ranks(timed_resident(steps))
+    hist = history(steps)                       # the SAME pass as ms_resident
+    lt = base.last_timing()
+    launches_per_step = lt["launches"] + (2 if world > 1 else 0)
+    path = lt["path"]
     # e2e: each step ends with a host synchronisation (the D2H result read).  Timed per step so that
     # the L2 flush of the small workloads stays outside the timed region, as in the resident leg.
     ms_e2e_local, wall_e2e = 0.0, 0.0
-    for _ in range(args.steps):
+    for _ in range(steps):
         if flush is not None:
             flush.fill_(1)
-        barrier()
+        bn.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
@@ -442,98 +561,161 @@ def run_b200(args, w):
         e1.synchronize()
         wall_e2e += time.perf_counter() - t0
         ms_e2e_local += e0.elapsed_time(e1)
-    ms_e2e = max_over_ranks(ms_e2e_local)
-    clocks = sampler.stop() if sampler else None
+    ms_e2e = bn.max_over_ranks(ms_e2e_local)
+    clocks = sampler.summary() if sampler else None
 
-    # roofline pass: the dominant kernel's own duration (events inside libtavec), per step
-    scan_ms, kinds_ms = [], {}
-    for _ in range(args.steps):
-        if flush is not None:
-            flush.fill_(1)
-        step_resident()
-        finish_resident()
-        t = base.last_timing()
-        scan_ms.append(t["scan_ms"])
-        per_step = {}
-        for name, ms in t["kernels"]:
-            per_step[name] = per_step.get(name, 0.0) + ms
-        per_step["search_total"] = t["total_ms"]
-        for name, ms in per_step.items():
-            kinds_ms.setdefault(name, []).append(ms)
-    kernel_ms = statistics.fmean(scan_ms)
-    breakdown = {name: statistics.fmean(v) for name, v in kinds_ms.items()}
+    # sustained: >= sustain_s seconds of back-to-back steps (the power cap engages after ~50 ms)
+    sustained = None
+    if sustain_s > 0 and flush is None:
+        per_step_s = max(ms_resident / steps / 1e3, 1e-5)
+        n_sus = int(min(max(sustain_s / per_step_s, 64), 200_000))
+        mark = sampler.mark() if sampler else 0
+        ms_sus = bn.max_over_ranks(timed_resident(n_sus))
+        h = history(64)
+        sus_clocks = sampler.summary(mark) if sampler else None
+        sustained = {"steps": n_sus, "seconds": ms_sus / 1e3, "ms_per_step": ms_sus / n_sus,
+                     "kernel_ms": statistics.fmean(h["main"]) if h["main"] else None,
+                     "sm_mhz": sus_clocks["sm_mhz"] if sus_clocks else None,
+                     "reasons": sus_clocks["reasons"] if sus_clocks else None}
+    if sampler:
+        sampler.stop()
 
-    # sanity: the result of the last step is well-formed
+    # the result of a last step: well-formed, and equal to the oracle's for sampled queries
     items, scores, counts = step_resident()
     finish_resident()
     torch.cuda.synchronize()
     assert int(counts.min()) == min(k, rows) and bool((scores[:, :-1] >= scores[:, 1:]).all())
     assert int(items.min()) >= 0 and int(items.max()) < rows
+    parity_checked, parity_note = False, "skipped"
+    if parity:
+        parity_checked, parity_note = check_parity(bn, corpus, lo, qn, items, scores, counts, k, w["min_score"], storage)
 
+    del corpus, base, sharded
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
-    peaks = load_peaks()
-    ms_step = ms_resident / args.steps
+    peaks = bn.peaks
+    ms_step = ms_resident / steps
     qps = batch / (ms_step / 1e3)
-    e2e_ms_step = ms_e2e / args.steps
+    e2e_ms_step = ms_e2e / steps
+    kernel_ms = statistics.fmean(hist["main"]) if hist["main"] else float("nan")
+    breakdown = {name_: statistics.fmean(v) for name_, v in hist.items() if v}
     # per-GPU dominant kernel: this rank's shard is read once per pass of the kernel
     passes = 1 if path in ("mma", "mma_split") else -(-batch // 8)
     algo_bytes = algorithmic_bytes(hi - lo, dim, storage, batch, k)
     algo_launch_bytes = (hi - lo) * dim * ELEM[storage] * passes + batch * dim * 4 + batch * k * 12
     achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
+    flops = 2.0 * batch * (hi - lo) * dim
+    tensor_bound = path in ("mma", "mma_split") and flops / (peaks["bf16_tflops"] or 1.6e3) / 1e12 > \
+        algo_bytes / peaks["hbm_gbs"] / 1e9 * 1.25
     out = {
-        "metric": "queries/sec, top-k cosine (VectorBase.fuzzy_lookup_embedding) on "
-                  f"{rows}x{dim} {storage}, batch {batch}, top-{k}",
-        "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_string(w),
+        "value": qps, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": {"float32": "f32", "bfloat16": "bf16", "float16": "f16"}[storage] + " in, f32 accumulate",
         "data": "synthetic (unit-norm gaussian rows, generated on device; seeds in bench.py)",
-        "config": {**workload_config(args, w, world), "path": path},
+        "config": workload_config(w, world),
+        "path": path,
         "gb_per_s": algorithmic_bytes(rows, dim, storage, batch, k) / (ms_step / 1e3) / 1e9,
         "e2e": {"value": batch / (e2e_ms_step / 1e3), "unit": "queries/s",
                 "h2d_bytes_per_step": batch * dim * 4, "d2h_bytes_per_step": batch * k * 12 + batch * 4,
-                "ms_per_step": e2e_ms_step, "wall_ms_per_step": wall_e2e * 1e3 / args.steps,
+                "ms_per_step": e2e_ms_step, "wall_ms_per_step": wall_e2e * 1e3 / steps,
                 "api": "VectorBase.search_arrays(host float32 queries) -> host int64/float32 hits"},
-        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches": launches_per_step * steps,
         "exact_fallback_queries": fallbacks[0],
+        "parity_checked": parity_checked, "parity": parity_note,
         "roofline": {
             "bound": "hbm", "kernel": "scan_rows_kernel" if path == "scan" else "mma_topk_kernel (" + path + ")",
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "of": peaks["source"], "traffic": load_ncu_traffic(args.workload, path, world, rows),
+            "of": peaks["source"], "traffic": load_ncu_traffic(name, path, world, rows),
             "kernel_ms_per_step": kernel_ms,
             "per_step_ms_by_kernel_kind": breakdown,
             "algorithmic_bytes_per_step": algo_bytes,
             "bytes_actually_requested_per_step": algo_launch_bytes,
-            "note": "achieved = algorithmic bytes (corpus shard read once per batch) / event-timed duration of "
-                    "the dominant kernel (the MAIN launch of the tcgen05 kernel, or the row-scan kernel) per step" + ("" if passes == 1 else
+            "note": "achieved = algorithmic bytes (corpus shard read once per batch) / duration of the dominant "
+                    "kernel (the MAIN launch of the tcgen05 kernel, or the row-scan kernel), CUDA events recorded by "
+                    "libtavec around it inside the timed region of `value` (same pass)" + ("" if passes == 1 else
                     f"; the row-scan path re-reads the corpus once per 8 queries ({passes} passes)"),
         },
         "clocks": clocks,
     }
-    if peaks.get("bf16_tflops"):
-        flops = 2.0 * batch * (hi - lo) * dim
-        out["roofline"]["tensor_tflops"] = flops / (kernel_ms / 1e3) / 1e12
-        out["roofline"]["tensor_frac_of_burst"] = out["roofline"]["tensor_tflops"] / peaks["bf16_tflops"]
-    if world == 1 and not args.no_cpu_baseline:
-        cb = cpu_reference_leg(w, args.cpu_sample_rows, args.cpu_sample_queries)
-        out["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample", "batched_sgemm_value")}
-        out["cpu_baseline"]["sample_gbs"] = cb["sample_gbs"]
-    print(json.dumps(out), file=_RESULT_OUT, flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if peaks.get("bf16_tflops") and path in ("mma", "mma_split"):
+        rf = out["roofline"]
+        rf["tensor_tflops"] = flops / (kernel_ms / 1e3) / 1e12
+        rf["tensor_frac_of_burst"] = rf["tensor_tflops"] / peaks["bf16_tflops"]
+        if tensor_bound:
+            # arithmetic intensity well above the ridge: the tensor pipe, not HBM, bounds this shape
+            rf["hbm_gbs"], rf["hbm_frac"] = rf["achieved"], rf["frac"]
+            rf.update({"bound": "tensor", "achieved": rf["tensor_tflops"], "peak": peaks["bf16_tflops"],
+                       "unit": "TFLOP/s", "frac": rf["tensor_frac_of_burst"]})
+    if sustained:
+        s_ach = algo_bytes / (sustained["kernel_ms"] / 1e3) / 1e9 if sustained["kernel_ms"] else None
+        out["roofline"]["sustained"] = {
+            **sustained, "achieved": s_ach, "frac": s_ach / peaks["hbm_gbs"] if s_ach else None,
+            "value": batch / (sustained["ms_per_step"] / 1e3),
+            "note": "same measurement over >= 2 s of back-to-back steps (kernel_ms = mean of the last 64): the "
+                    "figure under the 1 kW power cap"}
+        if peaks.get("bf16_tflops_sustained") and sustained["kernel_ms"]:
+            out["roofline"]["sustained"]["tensor_frac_of_sustained"] = \
+                flops / (sustained["kernel_ms"] / 1e3) / 1e12 / peaks["bf16_tflops_sustained"]
+    if cpu and world == 1:
+        leg = cpu_reference_leg(w, warmup=3, timed=cpu_queries, want_batched=True)
+        out["cpu_baseline"] = cpu_baseline_block(leg)
+    return out
+
+
+def check_parity(bn, corpus, lo, qn, items, scores, counts, k, min_score, storage):
+    """4 queries of the final step vs the blocked numpy oracle over the DEVICE corpus (each rank its
+    own shard, lists merged like shards), at the contract tolerances (scores 1e-4, ties 2e-6)."""
+    from oracle import vectorbase_oracle as O
+    from tests.parity import assert_hits_match, blocked_oracle_lookup
+
+    torch = bn.torch
+    b = len(qn)
+    pick = sorted({0, b // 3, (2 * b) // 3, b - 1})
+    q_pick = O.round_to_storage(qn[pick], storage)      # the device rounds queries to the storage dtype
+    local = blocked_oracle_lookup(corpus, q_pick, k, min_score, row_offset=lo)
+    if bn.world > 1:
+        gathered = [None] * bn.world
+        bn.dist.all_gather_object(gathered, [[(h.item, h.score) for h in hits] for hits in local])
+        if bn.rank != 0:
+            return True, "checked on rank 0"
+        local = [O.merge_shard_hits([[O.Hit(i, s) for i, s in shard[j]] for shard in gathered], k)
+                 for j in range(len(pick))]
+    it, sc, ct = items.cpu().numpy(), scores.cpu().numpy(), counts.cpu().numpy()
+    for j, qi in enumerate(pick):
+        got = {"items": it[qi, : ct[qi]].tolist(), "scores": sc[qi, : ct[qi]].tolist()}
+        assert_hits_match(got, local[j], score_tol=1e-4, tie_tol=2e-6, min_score=min_score,
+                          what=f"bench parity q{qi}")
+    return True, f"queries {pick} of the final step == blocked numpy oracle (scores 1e-4, ties 2e-6)"
+
+
+def run_b200(args, w):
+    bn = Bench(args)
+    force = None if args.path == "auto" else args.path
+    out = measure(bn, args.workload, w, args.steps, args.warmup, force=force, sustain_s=args.sustain_seconds,
+                  parity=not args.no_parity, cpu=not args.no_cpu_baseline, cpu_queries=args.cpu_queries)
+    # the other BASELINE configs ride along so that the driver's records carry them
+    secondary = {}
+    if not args.no_secondary and args.workload == "c3" and args.rows is None:
+        names = ["c1", "c2", "c5"] if bn.world == 1 else (["c4"] if bn.world == 8 else [])
+        for name in names:
+            sw = dict(WORKLOADS[name])
+            res = measure(bn, name, sw, steps=max(args.steps, 10), warmup=max(args.warmup, 3), sustain_s=0.0,
+                          parity=not args.no_parity, cpu=not args.no_cpu_baseline, cpu_queries=args.cpu_queries)
+            if res is not None:
+                keep = ("metric", "value", "unit", "ms_per_step", "path", "e2e", "roofline", "cpu_baseline",
+                        "parity_checked", "exact_fallback_queries", "gpu_launches", "config")
+                secondary[name] = {kk: res[kk] for kk in keep if kk in res}
+    if out is not None:
+        if secondary:
+            out["secondary"] = secondary
+        print(json.dumps(out), file=_RESULT_OUT, flush=True)
+    bn.close()
 
 
 _RESULT_OUT = sys.stdout
-
-
-class _NullModel:
-    model_name = "bench-null"
-
-    def add_embedding(self, key, embedding):
-        return None
 
 
 def main():

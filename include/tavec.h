@@ -17,7 +17,8 @@
  * failure.  There is no CPU fallback anywhere behind this ABI: without a CUDA device
  * every compute entry point fails with TAV_ERR_CUDA.
  *
- * Threading: an index may be used from one thread at a time.  Work is enqueued on the
+ * Threading: calls on one index are serialised by a mutex inside the library (ctypes releases
+ * the GIL); different indexes are independent.  Work is enqueued on the
  * caller's stream (`stream`, a cudaStream_t passed as void*; NULL = the CUDA legacy default
  * stream, as everywhere in the CUDA runtime).  Entry points that take host output pointers
  * synchronise that stream before returning; with TAV_OUTPUTS_ON_DEVICE they return as soon
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TAV_ABI_VERSION 1
+#define TAV_ABI_VERSION 2
 
 typedef struct tav_index tav_index; /* opaque: device corpus + search workspace */
 
@@ -66,7 +67,18 @@ enum tav_search_flags {
     /* Fully asynchronous tensor-core search (needs both ..._ON_DEVICE flags): the check whether
      * some query must be redone by the exact row scan — a host synchronisation — is left to
      * tav_finish_search.  Until then the outputs of such (rare) queries are not final. */
-    TAV_DEFER_RETRY = 16
+    TAV_DEFER_RETRY = 16,
+    /* Predicate / post-filter pushdown (vectorbase.py:191-201, storage/sqlite/messageindex.py:
+     * 296-326): only rows whose bit is set in the mask given to tav_set_row_mask may be returned. */
+    TAV_USE_ROW_MASK = 32,
+    /* Among exactly equal scores return the LOWER row first (the reference's stable sort on its
+     * predicate path, vectorbase.py:200); default is higher row first (its argsort path, :184-187).
+     * Row-scan kernels only. */
+    TAV_TIES_LOW_FIRST = 64,
+    /* Do not use the single-launch form of the row scan (one host query, host outputs: the query
+     * rides in the kernel parameters and the last CTA merges); tests use it to reach the two-kernel
+     * form with one query. */
+    TAV_NO_FUSED_SCAN = 128
 };
 
 int tav_abi_version(void);
@@ -120,14 +132,17 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
                int flags, const int64_t* subset, int64_t subset_len, int64_t item_offset,
                int64_t* out_items, float* out_scores, int32_t* out_counts, void* stream);
 
-/* Completes a TAV_DEFER_RETRY search: synchronises `stream`, redoes flagged queries exactly into
- * the same outputs and reports how many (*redone).  The arguments repeat the deferred call.
- * Several deferred searches may precede one finish; if an EARLIER one needed the fallback the
- * call fails with TAV_ERR_STATE (its outputs were never corrected).  No-op when nothing is
- * pending. */
-int tav_finish_search(tav_index* ix, const float* queries_device, int n_queries, int k, float min_score,
-                      int64_t item_offset, int64_t* out_items, float* out_scores, int32_t* out_counts,
-                      void* stream, int* redone);
+/* Completes EVERY outstanding TAV_DEFER_RETRY search of the index: synchronises `stream`, redoes
+ * each search's flagged queries exactly into that search's own outputs and reports how many
+ * (*redone).  The caller keeps the query and output buffers of deferred searches alive until
+ * then.  Up to 64 searches may be outstanding (a 65th finishes the earlier ones first).  No-op
+ * when nothing is pending. */
+int tav_finish_search(tav_index* ix, void* stream, int* redone);
+
+/* Row mask for TAV_USE_ROW_MASK: `n_rows` bits (bit r of word r/32 = row r allowed), host or
+ * device memory; n_rows must equal tav_size().  Kept on the device until the rows change
+ * (tav_clear / tav_adopt_device drop it; appends invalidate it) or n_rows == 0 clears it. */
+int tav_set_row_mask(tav_index* ix, const uint32_t* bits, int64_t n_rows, int on_device, void* stream);
 
 /*
  * Merge step of the row-sharded search: `n_lists` per-shard results of
@@ -145,6 +160,16 @@ int tav_merge_topk(int device, int n_lists, int n_queries, int k, const int64_t*
                    const float* scores, const int32_t* counts, int64_t items_stride,
                    int64_t scores_stride, int64_t counts_stride, int64_t* out_items,
                    float* out_scores, int32_t* out_counts, void* stream);
+
+/*
+ * Chunk -> message fold of hit lists, on the device, in place (storage/memory/messageindex.py:
+ * 185-207 `to_scored_message_ordinals`; the reference folds AFTER the top-k over chunks): walking
+ * each query's hits in score order, the first hit of a group keeps its score, later hits of the
+ * same group are dropped; items become group ordinals `row_to_group[item - item_offset]` (device
+ * int32 [n_rows]); counts are updated, tails padded with -1 / 0.  k <= 8192.
+ */
+int tav_fold_groups(int device, int n_queries, int k, const int32_t* row_to_group, int64_t n_rows,
+                    int64_t item_offset, int64_t* items, float* scores, int32_t* counts, void* stream);
 
 /* Verification aid for the tensor-core path: every raw dot product it computes,
  * out_device[n_queries, size] float32 (device memory); float32 indexes go through their fp16 planes.  `flags` may
@@ -167,6 +192,13 @@ int tav_last_timing(tav_index* ix, float* scan_ms, float* total_ms, int* launche
 /* Per-kernel durations of the last tav_search, in launch order (up to `capacity` entries;
  * *n = number recorded): kinds[i] = 0 dominant kernel, 1 sample pass, 2 auxiliary kernel. */
 int tav_timing_breakdown(tav_index* ix, float* ms, int* kinds, int capacity, int* n);
+
+/* Device times of the last (up to 64, up to `capacity`) timed searches, oldest first: per search
+ * the dominant kernel, the sample pass, the auxiliary kernels and first-launch-to-last-byte.
+ * Lets a benchmark time its steps back to back and read the per-kernel times of the SAME pass
+ * afterwards.  Synchronises on the last search's events. */
+int tav_timing_history(tav_index* ix, int capacity, float* main_ms, float* sample_ms, float* aux_ms,
+                       float* total_ms, int* n);
 
 #ifdef __cplusplus
 }

@@ -61,3 +61,24 @@ def assert_hits_match(got, want, *, score_tol=SCORE_TOL, tie_tol=TIE_TOL, min_sc
     for pos, (gi, wi) in enumerate(zip(g_items, w_items)):
         if gi != wi:
             assert abs(g_scores[pos] - w_scores[pos]) <= tie_tol, f"order differs at {pos}; {ctx}"
+
+
+def blocked_oracle_lookup(corpus, queries, k, min_score=0.0, row_offset=0, block_rows=1_000_000):
+    """Oracle top-k over a DEVICE-resident corpus too large to score in one piece: the rows come back
+    in ``block_rows`` blocks as float32 (storage -> float32 is exact), ``oracle.lookup`` — the
+    reference's np.dot / clip / flatnonzero / argpartition — runs per block and the per-block lists
+    are merged like shards (exact: top-k of a union of exact per-block top-k lists).  ``corpus`` is a
+    torch CUDA tensor [N, D]; ``queries`` float32 numpy [B, D].  Returns one list of Hits per query."""
+    import torch
+
+    from oracle import vectorbase_oracle as O
+
+    parts = [[] for _ in range(len(queries))]
+    n = corpus.shape[0]
+    for lo in range(0, n, block_rows):
+        block = corpus[lo:lo + block_rows].to(torch.float32).cpu().numpy()
+        for j, q in enumerate(queries):
+            hits = O.lookup(block, q, k, min_score)
+            parts[j].append([O.Hit(h.item + lo + row_offset, h.score) for h in hits])
+        del block
+    return [O.merge_shard_hits(p, k) for p in parts]

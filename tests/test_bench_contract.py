@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def run_bench(*extra, env=None):
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
-           "--cpu-sample-rows", "20000", "--cpu-sample-queries", "3", *extra]
+           "--rows", "20000", *extra]
     return subprocess.run(cmd, capture_output=True, text=True, env={**os.environ, **(env or {})}, timeout=300)
 
 
@@ -29,9 +29,18 @@ def test_reference_arm_prints_one_json_line_with_contract_keys():
         assert key in out, key
     assert out["unit"] == "queries/s" and out["higher_is_better"] is True and out["vs_baseline"] is None
     assert out["steps"] == 2 and out["warmup"] == 1 and out["value"] > 0
-    assert out["config"]["workload"].startswith("10M x 768") and out["config"]["rows"] == 10_000_000
-    assert out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["cores"] >= 1
+    assert out["config"]["workload"].startswith("10M x 768") and out["config"]["rows"] == 20_000
+    assert out["cpu_baseline"]["kind"] in ("reference", "port") and out["cpu_baseline"]["cores"] >= 1
+    assert "FULL corpus 20000 x 768" in out["cpu_baseline"]["sample"]
+    # the SAME metric string as the repo arm prints, so that the driver can divide one by the other
+    sys.path.insert(0, ROOT)
+    import bench
+
+    w = dict(bench.WORKLOADS["c3"], rows=20_000)
+    assert out["metric"] == bench.metric_string(w)
+    assert out["config"] == {**bench.workload_config(dict(w, desc=out["config"]["workload"]), 1)}
     assert out["cpu_baseline"]["value"] == out["value"]
+    assert abs(out["ms_per_step"] - 256 * 1e3 / out["value"]) < 1e-6 * out["ms_per_step"]
     assert out["e2e"] == {"value": out["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

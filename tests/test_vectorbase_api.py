@@ -202,7 +202,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"libtavec.so does not export {name}"
         assert name in _capi.SIGNATURES, f"ctypes binding lacks {name}"
     assert set(_capi.SIGNATURES) == set(names)
-    assert lib.tav_abi_version() == 1
+    assert lib.tav_abi_version() == _capi.ABI_VERSION == 2
 
 
 def test_no_gpu_means_loud_failure_not_cpu_fallback():

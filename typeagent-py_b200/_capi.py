@@ -19,6 +19,8 @@ DTYPE_NAMES = {v: k for k, v in DTYPE_CODES.items()}
 
 TAV_NORMALIZE = 1
 TAV_QUERIES_ON_DEVICE, TAV_OUTPUTS_ON_DEVICE, TAV_FORCE_SCAN, TAV_FORCE_MMA, TAV_DEFER_RETRY = 1, 2, 4, 8, 16
+TAV_USE_ROW_MASK, TAV_TIES_LOW_FIRST, TAV_NO_FUSED_SCAN = 32, 64, 128
+ABI_VERSION = 2
 
 TAV_ERR_INVALID, TAV_ERR_CUDA, TAV_ERR_OOM, TAV_ERR_RANGE, TAV_ERR_STATE = -1, -2, -3, -4, -5
 
@@ -44,8 +46,11 @@ SIGNATURES = {
     "tav_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int,
                              C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_void_p]),
-    "tav_finish_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int64,
-                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "tav_finish_search": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "tav_set_row_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "tav_fold_groups": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tav_timing_history": (C.c_int, [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, _f32p, C.POINTER(C.c_int)]),
     "tav_merge_topk": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int64, C.c_int64, C.c_int64,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -80,8 +85,8 @@ def load() -> C.CDLL:
                 raise RuntimeError(f"libtavec.so does not export {name}") from e
             fn.restype = restype
             fn.argtypes = argtypes
-        if lib.tav_abi_version() != 1:
-            raise RuntimeError(f"libtavec.so ABI version {lib.tav_abi_version()} != 1; rebuild")
+        if lib.tav_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"libtavec.so ABI version {lib.tav_abi_version()} != {ABI_VERSION}; rebuild")
         _lib = lib
     return _lib
 

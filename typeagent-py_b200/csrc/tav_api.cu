@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -83,9 +84,36 @@ struct PinBuf {
     }
 };
 
-constexpr int kMaxTimedChunks = 64;
+constexpr int kMaxTimedKernels = 12;   // event pairs per search (more kernels than that go untimed)
+constexpr int kHistory = 64;           // timed searches remembered (tav_timing_history)
+constexpr int kMaxPending = 64;        // deferred searches that may await one tav_finish_search
 constexpr size_t kPinnedStageLimit = size_t(8) << 20;  // payloads above this go straight from user memory
 constexpr size_t kZeroCopyOutLimit = size_t(16) << 10; // results up to this size are written to host memory by the kernels
+constexpr size_t kAppendStageBytes = size_t(32) << 20; // pinned double buffer of the bulk-load path
+
+// CUDA events around one search (created lazily, when timing is first enabled)
+struct TimedSearch {
+    cudaEvent_t total[2] = {nullptr, nullptr};
+    cudaEvent_t ev[kMaxTimedKernels][2];
+    int kind[kMaxTimedKernels];  // 0 dominant kernel, 1 sample pass, 2 auxiliary
+    int used = 0;
+    int launches = 0;
+    int path = 0;
+    bool valid = false;
+};
+
+// a TAV_DEFER_RETRY search whose "redo exactly" flags have not been looked at yet
+struct Pending {
+    const float* queries;  // device
+    int nq, k;
+    float floor;
+    int64_t item_offset;
+    int64_t* items;
+    float* scores;
+    int32_t* counts;
+    int slot;
+    bool split, masked;
+};
 
 }  // namespace tav
 
@@ -100,40 +128,52 @@ struct tav_index {
     int64_t capacity = 0;
     void* rows = nullptr;  // [capacity, dim] storage dtype
     bool adopted = false;
+    std::mutex mu;         // one call at a time per index (ctypes releases the GIL)
 
     // search workspace
     DevBuf queries;     // float32 [n_queries, dim]
     DevBuf subset;      // int64 [subset_len]
     DevBuf cand_keys;   // [qb, cand_stride] uint64
-    DevBuf cand_count;  // [qb] uint32 + [qb] uint64 bounds
-    DevBuf out_pack;    // device result staging for host outputs: [items | scores | counts | retry]
+    DevBuf cand_count;  // [8] uint64 bounds | [8] uint32 counters | fused ticket
+    DevBuf out_pack;    // device result staging for host outputs: [items | scores | counts]
     PinBuf pin_in;      // pinned staging: queries (+ subset) on the way in
-    PinBuf pin_out;     // pinned staging: packed results on the way out
+    PinBuf pin_out;     // pinned staging: packed results on the way out (+ the completion word)
+    PinBuf pin_append[2];             // bulk load: pinned double buffer
+    cudaEvent_t ev_append[2] = {nullptr, nullptr};
     cudaEvent_t ev_pin_in = nullptr;  // completion of the last H2D that read pin_in
     bool pin_in_busy = false;
+    uint32_t done_seq = 0;            // completion word sequence of the single-launch form
     DevBuf staging;     // append: source rows before conversion
     DevBuf mma_ws;      // tensor-core path workspace
-    DevBuf retry;       // int32 [n_queries] flags of the last tensor-core search + [1] running total at the end
-    int retry_capacity = 0;      // queries the flag array is sized for
+    // "redo exactly" bookkeeping of the tensor-core path, one slot per outstanding search:
+    // [kMaxPending][2] int32 {flagged queries, a query value left the fp16 range} | [kMaxPending][retry_cap] flags
+    DevBuf retry;
+    int retry_cap = 0;
+    std::vector<Pending> pending;
+    int next_slot = 0;
     // float32 indexes: the rows as two fp16 planes for the tensor-core path (built lazily,
-    // extended on append); split_flag[0] = a corpus value left the fp16 range (sticky),
-    // split_flag[1] = a query value did (per search)
+    // extended on append); split_flag[0] = a corpus value left the fp16 range
     DevBuf split_hi, split_lo, split_flag;
     int64_t split_rows = 0;      // rows [0, split_rows) of the planes are current
     int64_t split_cap = 0;
-    bool last_split = false;     // the last tensor-core search used the planes
-    int pending_queries = 0;     // > 0: a TAV_DEFER_RETRY search awaits tav_finish_search
+    // predicate pushdown: one bit per row (tav_set_row_mask)
+    DevBuf row_mask;
+    int64_t row_mask_rows = 0;   // 0 = no mask set
 
-    // timing of the last search
-    cudaEvent_t ev_total[2] = {nullptr, nullptr};
-    cudaEvent_t ev_chunk[kMaxTimedChunks][2];
-    int ev_kind[kMaxTimedChunks];  // 0 dominant kernel, 1 sample pass, 2 auxiliary
-    int timed_chunks = 0;
-    int launches = 0;
-    int path = 0;
-    bool timing_valid = false;
-    bool timing_on = false;  // record CUDA events around kernels (tav_set_timing)
+    // timing
+    TimedSearch* hist = nullptr; // [kHistory], created by tav_set_timing(1)
+    int64_t search_seq = 0;      // searches timed so far
+    TimedSearch untimed;         // path / launch count of the last search when timing is off
+    bool timing_on = false;
 };
+
+static TimedSearch* cur_timed(tav_index* ix) {
+    return ix->timing_on && ix->hist ? &ix->hist[(ix->search_seq) % kHistory] : nullptr;
+}
+static TimedSearch* last_timed(tav_index* ix) {
+    if (ix->timing_on && ix->hist && ix->search_seq > 0) return &ix->hist[(ix->search_seq - 1) % kHistory];
+    return &ix->untimed;
+}
 
 // The pinned input staging may still be the source of an in-flight H2D copy when the previous
 // search returned without synchronising (device outputs): wait for that copy before reuse.
@@ -149,6 +189,21 @@ static cudaError_t pin_in_acquire(tav_index* ix, size_t bytes) {
 static int set_device(const tav_index* ix) {
     TAV_CUDA(cudaSetDevice(ix->device));
     return TAV_OK;
+}
+
+static int finish_pending(tav_index* ix, cudaStream_t s, int* redone);
+
+static void destroy_history(tav_index* ix) {
+    if (!ix->hist) return;
+    for (int h = 0; h < kHistory; ++h) {
+        for (auto& ev : ix->hist[h].total)
+            if (ev) cudaEventDestroy(ev);
+        for (auto& pr : ix->hist[h].ev)
+            for (auto& ev : pr)
+                if (ev) cudaEventDestroy(ev);
+    }
+    delete[] ix->hist;
+    ix->hist = nullptr;
 }
 
 extern "C" {
@@ -194,16 +249,11 @@ int tav_create(int device, int dim, int store_dtype, int index_flags, int64_t re
     ix->dim = dim;
     ix->dtype = store_dtype;
     ix->flags = index_flags;
-    for (auto& pr : ix->ev_chunk) pr[0] = pr[1] = nullptr;
-    cudaError_t ce = cudaEventCreate(&ix->ev_total[0]);
-    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ix->ev_pin_in, cudaEventDisableTiming);
-    if (ce == cudaSuccess) ce = cudaEventCreate(&ix->ev_total[1]);
-    for (int i = 0; ce == cudaSuccess && i < kMaxTimedChunks; ++i) {
-        ce = cudaEventCreate(&ix->ev_chunk[i][0]);
-        if (ce == cudaSuccess) ce = cudaEventCreate(&ix->ev_chunk[i][1]);
-    }
+    cudaError_t ce = cudaEventCreateWithFlags(&ix->ev_pin_in, cudaEventDisableTiming);
+    for (int i = 0; ce == cudaSuccess && i < 2; ++i)
+        ce = cudaEventCreateWithFlags(&ix->ev_append[i], cudaEventDisableTiming);
     if (ce != cudaSuccess) {
-        set_error("tav_create: stream/event creation failed: %s", cudaGetErrorString(ce));
+        set_error("tav_create: event creation failed: %s", cudaGetErrorString(ce));
         tav_destroy(ix);
         return TAV_ERR_CUDA;
     }
@@ -224,23 +274,23 @@ int tav_destroy(tav_index* ix) {
     cudaSetDevice(ix->device);
     cudaDeviceSynchronize();  // searches may still be in flight on the caller's streams
     if (ix->rows && !ix->adopted) cudaFree(ix->rows);
-    for (DevBuf* b : {&ix->queries, &ix->subset, &ix->cand_keys, &ix->cand_count, &ix->out_pack,
-                      &ix->staging, &ix->mma_ws, &ix->retry, &ix->split_hi, &ix->split_lo, &ix->split_flag})
+    for (DevBuf* b : {&ix->queries, &ix->subset, &ix->cand_keys, &ix->cand_count, &ix->out_pack, &ix->staging,
+                      &ix->mma_ws, &ix->retry, &ix->split_hi, &ix->split_lo, &ix->split_flag, &ix->row_mask})
         b->release();
     ix->pin_in.release();
     ix->pin_out.release();
-    for (auto& ev : ix->ev_total)
-        if (ev) cudaEventDestroy(ev);
+    for (auto& b : ix->pin_append) b.release();
     if (ix->ev_pin_in) cudaEventDestroy(ix->ev_pin_in);
-    for (auto& pr : ix->ev_chunk)
-        for (auto& ev : pr)
-            if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ix->ev_append)
+        if (ev) cudaEventDestroy(ev);
+    destroy_history(ix);
     delete ix;
     return TAV_OK;
 }
 
 int tav_clear(tav_index* ix) {
     if (!ix) return TAV_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ix->mu);
     if (ix->adopted) {
         ix->rows = nullptr;
         ix->adopted = false;
@@ -248,11 +298,15 @@ int tav_clear(tav_index* ix) {
     }
     ix->size = 0;
     ix->split_rows = 0;
+    ix->row_mask_rows = 0;
+    if (ix->split_flag.p) {  // the sticky "a corpus value left the fp16 range" flag dies with the rows
+        cudaSetDevice(ix->device);
+        cudaMemset(ix->split_flag.p, 0, sizeof(int));
+    }
     return TAV_OK;
 }
 
-int tav_reserve(tav_index* ix, int64_t rows) {
-    if (!ix || rows < 0) return TAV_ERR_INVALID;
+static int reserve_locked(tav_index* ix, int64_t rows) {
     if (ix->adopted) {
         set_error("tav_reserve: index uses adopted device memory");
         return TAV_ERR_STATE;
@@ -285,12 +339,19 @@ int tav_reserve(tav_index* ix, int64_t rows) {
     return TAV_OK;
 }
 
+int tav_reserve(tav_index* ix, int64_t rows) {
+    if (!ix || rows < 0) return TAV_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    return reserve_locked(ix, rows);
+}
+
 int tav_append(tav_index* ix, const void* rows, int64_t n, int dim, int src_dtype,
                int src_on_device, void* stream) {
     if (!ix || n < 0 || dim <= 0 || !dtype_ok(src_dtype) || (n > 0 && !rows)) {
         set_error("tav_append: invalid argument");
         return TAV_ERR_INVALID;
     }
+    std::lock_guard<std::mutex> lock(ix->mu);
     if (ix->adopted) {
         set_error("tav_append: index uses adopted device memory");
         return TAV_ERR_STATE;
@@ -307,37 +368,53 @@ int tav_append(tav_index* ix, const void* rows, int64_t n, int dim, int src_dtyp
         int64_t want = std::max<int64_t>(ix->size + n, ix->capacity * 2);
         want = std::max<int64_t>(want, 1024);
         TAV_CUDA(cudaStreamSynchronize(s));
-        if (int rc = tav_reserve(ix, want)) return rc;
+        if (int rc = reserve_locked(ix, want)) return rc;
     }
     const size_t dst_row = static_cast<size_t>(ix->dim) * dtype_size(ix->dtype);
     const size_t src_row = static_cast<size_t>(ix->dim) * dtype_size(src_dtype);
     char* dst = static_cast<char*>(ix->rows) + static_cast<size_t>(ix->size) * dst_row;
     const bool plain = (src_dtype == ix->dtype) && !(ix->flags & TAV_NORMALIZE);
-    if (plain) {
-        TAV_CUDA(cudaMemcpyAsync(dst, rows, static_cast<size_t>(n) * src_row,
-                                 src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-    } else if (src_on_device) {
-        TAV_CUDA(launch_convert(rows, src_dtype, dst, ix->dtype, n, ix->dim,
-                                (ix->flags & TAV_NORMALIZE) ? 1 : 0, s));
+    const int norm = (ix->flags & TAV_NORMALIZE) ? 1 : 0;
+    if (src_on_device) {
+        if (plain)
+            TAV_CUDA(cudaMemcpyAsync(dst, rows, static_cast<size_t>(n) * src_row, cudaMemcpyDeviceToDevice, s));
+        else
+            TAV_CUDA(launch_convert(rows, src_dtype, dst, ix->dtype, n, ix->dim, norm, s));
     } else {
-        // host source needing conversion: stage through a bounded device buffer, chunk by chunk
-        const int64_t chunk_rows = std::max<int64_t>(1, (64ll << 20) / static_cast<int64_t>(src_row));
-        TAV_CUDA(ix->staging.ensure(static_cast<size_t>(std::min(n, chunk_rows)) * src_row));
-        for (int64_t done = 0; done < n; done += chunk_rows) {
+        // Host source (bulk load at open, storage/sqlite/messageindex.py:33-45; incremental appends):
+        // through a pinned double buffer, so that the H2D copies are truly asynchronous and the host
+        // memcpy of chunk i+1 overlaps the DMA (+ conversion kernel) of chunk i.
+        const int64_t chunk_rows = std::max<int64_t>(1, static_cast<int64_t>(kAppendStageBytes / src_row));
+        const size_t stage_bytes = static_cast<size_t>(std::min(n, chunk_rows)) * src_row;
+        if (!plain) TAV_CUDA(ix->staging.ensure(2 * stage_bytes));
+        int b = 0;
+        bool used[2] = {false, false};
+        for (int64_t done = 0; done < n; done += chunk_rows, b ^= 1) {
             const int64_t m = std::min(chunk_rows, n - done);
-            TAV_CUDA(cudaMemcpyAsync(ix->staging.p, static_cast<const char*>(rows) + done * src_row,
-                                     static_cast<size_t>(m) * src_row, cudaMemcpyHostToDevice, s));
-            TAV_CUDA(launch_convert(ix->staging.p, src_dtype, dst + done * dst_row, ix->dtype, m,
-                                    ix->dim, (ix->flags & TAV_NORMALIZE) ? 1 : 0, s));
+            const size_t bytes = static_cast<size_t>(m) * src_row;
+            if (used[b]) TAV_CUDA(cudaEventSynchronize(ix->ev_append[b]));
+            TAV_CUDA(ix->pin_append[b].ensure(stage_bytes));
+            memcpy(ix->pin_append[b].p, static_cast<const char*>(rows) + done * src_row, bytes);
+            if (plain) {
+                TAV_CUDA(cudaMemcpyAsync(dst + done * dst_row, ix->pin_append[b].p, bytes, cudaMemcpyHostToDevice, s));
+            } else {
+                char* stage = static_cast<char*>(ix->staging.p) + static_cast<size_t>(b) * stage_bytes;
+                TAV_CUDA(cudaMemcpyAsync(stage, ix->pin_append[b].p, bytes, cudaMemcpyHostToDevice, s));
+                TAV_CUDA(launch_convert(stage, src_dtype, dst + done * dst_row, ix->dtype, m, ix->dim, norm, s));
+            }
+            TAV_CUDA(cudaEventRecord(ix->ev_append[b], s));
+            used[b] = true;
         }
+        // the caller's buffer was fully consumed by the memcpys above; the pinned buffers are
+        // re-acquired through their events, so no synchronisation is needed here
     }
-    if (!src_on_device) TAV_CUDA(cudaStreamSynchronize(s));  // the host buffer may be reused
     ix->size += n;
     return TAV_OK;
 }
 
 int tav_adopt_device(tav_index* ix, void* device_rows, int64_t n, int dim) {
     if (!ix || n < 0 || dim <= 0 || (n > 0 && !device_rows)) return TAV_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ix->mu);
     if (ix->flags & TAV_NORMALIZE) {
         set_error("tav_adopt_device: not available on a TAV_NORMALIZE index (rows are used as is)");
         return TAV_ERR_STATE;
@@ -350,14 +427,16 @@ int tav_adopt_device(tav_index* ix, void* device_rows, int64_t n, int dim) {
         set_error("tav_adopt_device: pointer must be 16-byte aligned");
         return TAV_ERR_INVALID;
     }
+    cudaSetDevice(ix->device);
     if (ix->rows && !ix->adopted) {
-        cudaSetDevice(ix->device);
         cudaDeviceSynchronize();
         cudaFree(ix->rows);
     }
     ix->dim = dim;
     ix->rows = device_rows;
     ix->split_rows = 0;
+    if (ix->split_flag.p) cudaMemset(ix->split_flag.p, 0, sizeof(int));
+    ix->row_mask_rows = 0;
     ix->adopted = true;
     ix->size = n;
     ix->capacity = n;
@@ -371,6 +450,7 @@ int tav_device(const tav_index* ix) { return ix ? ix->device : -1; }
 
 int tav_read_rows(tav_index* ix, int64_t first, int64_t n, float* out_host, void* stream) {
     if (!ix || n < 0 || (n > 0 && !out_host)) return TAV_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ix->mu);
     if (first < 0 || first + n > ix->size) {
         set_error("tav_read_rows: rows [%lld, %lld) out of range (size %lld)", (long long)first,
                   (long long)(first + n), (long long)ix->size);
@@ -393,12 +473,59 @@ int tav_read_rows(tav_index* ix, int64_t first, int64_t n, float* out_host, void
     return TAV_OK;
 }
 
-// Row-scan search of queries [q0, q0+nq) (device float32), any k: passes of <= kPassK hits.
-static int scan_search(tav_index* ix, const float* d_queries, int nq_total, int k, float floor_score,
-                       const int64_t* d_subset, int64_t n_scan, int64_t item_offset,
-                       int64_t* d_items, float* d_scores, int32_t* d_counts,
-                       const int32_t* only_flagged, cudaStream_t s) {
-    (void)only_flagged;
+int tav_set_row_mask(tav_index* ix, const uint32_t* bits, int64_t n_rows, int on_device, void* stream) {
+    if (!ix || n_rows < 0 || (n_rows > 0 && !bits)) return TAV_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if (int rc = set_device(ix)) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!ix->pending.empty()) {  // an outstanding search may still need the old mask for its exact redo
+        int redone = 0;
+        if (int rc = finish_pending(ix, s, &redone)) return rc;
+    }
+    if (n_rows == 0) {
+        ix->row_mask_rows = 0;
+        return TAV_OK;
+    }
+    if (n_rows != ix->size) {
+        set_error("tav_set_row_mask: %lld bits for an index of %lld rows", (long long)n_rows, (long long)ix->size);
+        return TAV_ERR_INVALID;
+    }
+    // padded to whole 256-row tiles (the tensor-core epilogue reads one word per 32 rows of a tile)
+    const size_t words = static_cast<size_t>((n_rows + 255) / 256) * 8;
+    const size_t src_words = static_cast<size_t>((n_rows + 31) / 32);
+    TAV_CUDA(ix->row_mask.ensure(words * sizeof(uint32_t)));
+    TAV_CUDA(cudaMemsetAsync(ix->row_mask.p, 0, words * sizeof(uint32_t), s));
+    TAV_CUDA(cudaMemcpyAsync(ix->row_mask.p, bits, src_words * sizeof(uint32_t),
+                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    if (!on_device) TAV_CUDA(cudaStreamSynchronize(s));
+    ix->row_mask_rows = n_rows;
+    return TAV_OK;
+}
+
+}  // extern "C"
+
+static inline cudaError_t ev_record(cudaEvent_t& ev, cudaStream_t s) {
+    if (!ev) {
+        cudaError_t e = cudaEventCreate(&ev);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaEventRecord(ev, s);
+}
+
+// workspace of the row-scan kernels: [8] u64 bounds | [8] u32 counters | [1] u32 fused ticket, zeroed once
+static int ensure_scan_counters(tav_index* ix, cudaStream_t s) {
+    const size_t need = 8 * (sizeof(uint32_t) + sizeof(uint64_t)) + 64;
+    if (ix->cand_count.bytes < need) {
+        TAV_CUDA(ix->cand_count.ensure(need));
+        TAV_CUDA(cudaMemsetAsync(ix->cand_count.p, 0, ix->cand_count.bytes, s));
+    }
+    return TAV_OK;
+}
+
+// Row-scan search of nq_total queries (device float32), any k: passes of <= kPassK hits.
+static int scan_search(tav_index* ix, TimedSearch* ts, bool timing, const float* d_queries, int nq_total, int k, float floor_score,
+                       const int64_t* d_subset, int64_t n_scan, int64_t item_offset, int64_t* d_items,
+                       float* d_scores, int32_t* d_counts, const uint32_t* d_mask, int ties_low, cudaStream_t s) {
     const int pass_k = std::min(k, kPassK);
     int qb = scan_max_queries(ix->dim, pass_k);
     if (qb < 1) {
@@ -411,11 +538,7 @@ static int scan_search(tav_index* ix, const float* d_queries, int nq_total, int 
     const int grid = scan_grid(ix->device, ix->dtype, ix->dim, qb, pass_k, n_scan);
     const int cand_stride = grid * pass_k;
     TAV_CUDA(ix->cand_keys.ensure(static_cast<size_t>(qb) * cand_stride * sizeof(uint64_t)));
-    if (ix->cand_count.bytes < 8 * (sizeof(uint32_t) + sizeof(uint64_t)) + 64) {
-        // sized for the largest pass (8 queries) once, zeroed once; select_kernel re-zeroes the counters
-        TAV_CUDA(ix->cand_count.ensure(8 * (sizeof(uint32_t) + sizeof(uint64_t)) + 64));
-        TAV_CUDA(cudaMemsetAsync(ix->cand_count.p, 0, ix->cand_count.bytes, s));
-    }
+    if (int rc = ensure_scan_counters(ix, s)) return rc;
     uint64_t* d_bound = static_cast<uint64_t*>(ix->cand_count.p);
     uint32_t* d_count = reinterpret_cast<uint32_t*>(d_bound + 8);
     const int n_pass = (k + pass_k - 1) / pass_k;
@@ -440,12 +563,14 @@ static int scan_search(tav_index* ix, const float* d_queries, int nq_total, int 
             a.cand_stride = cand_stride;
             a.cand_count = d_count;
             a.grid = grid;
-            const bool timed = ix->timing_on && ix->timed_chunks < kMaxTimedChunks;
-            if (timed) TAV_CUDA(cudaEventRecord(ix->ev_chunk[ix->timed_chunks][0], s));
+            a.row_mask = d_mask;
+            a.ties_low = ties_low;
+            const bool timed = timing && ts && ts->used < kMaxTimedKernels;
+            if (timed) TAV_CUDA(ev_record(ts->ev[ts->used][0], s));
             TAV_CUDA(launch_scan(a, s));
             if (timed) {
-                ix->ev_kind[ix->timed_chunks] = 0;
-                TAV_CUDA(cudaEventRecord(ix->ev_chunk[ix->timed_chunks++][1], s));
+                ts->kind[ts->used] = 0;
+                TAV_CUDA(ev_record(ts->ev[ts->used++][1], s));
             }
             SelectArgs sel{};
             sel.cand_keys = a.cand_keys;
@@ -463,17 +588,16 @@ static int scan_search(tav_index* ix, const float* d_queries, int nq_total, int 
             sel.out_counts = d_counts + q0;
             sel.bound_out = n_pass > 1 ? d_bound : nullptr;
             sel.accumulate = pass > 0;
+            sel.ties_low = ties_low;
             TAV_CUDA(launch_select(sel, s));
-            ix->launches += 2;
+            if (ts) ts->launches += 2;
         }
     }
     return TAV_OK;
 }
 
-}  // extern "C"
-
 // float32 index -> fp16 hi/lo planes covering rows [0, size); returns TAV_ERR_OOM when they do not fit
-static int ensure_split_planes(tav_index* ix, cudaStream_t s) {
+static int ensure_split_planes(tav_index* ix, TimedSearch* ts, cudaStream_t s) {
     const size_t plane_row = static_cast<size_t>(ix->dim) * 2;
     if (ix->split_flag.bytes == 0) {
         TAV_CUDA(ix->split_flag.ensure(2 * sizeof(int)));
@@ -495,71 +619,79 @@ static int ensure_split_planes(tav_index* ix, cudaStream_t s) {
             return TAV_ERR_OOM;
         }
         ix->split_cap = cap;
-        TAV_CUDA(cudaMemsetAsync(ix->split_flag.p, 0, sizeof(int), s));
     }
     if (ix->split_rows < ix->size) {
+        if (ix->split_rows == 0) TAV_CUDA(cudaMemsetAsync(ix->split_flag.p, 0, sizeof(int), s));  // planes rebuilt from row 0
         const int64_t first = ix->split_rows, n = ix->size - first;
         TAV_CUDA(launch_split_rows(static_cast<const float*>(ix->rows) + first * ix->dim,
                                    static_cast<char*>(ix->split_hi.p) + static_cast<size_t>(first) * plane_row,
                                    static_cast<char*>(ix->split_lo.p) + static_cast<size_t>(first) * plane_row, n,
                                    ix->dim, static_cast<int*>(ix->split_flag.p), s));
         ix->split_rows = ix->size;
-        ix->launches += 1;
+        if (ts) ts->launches += 1;
     }
     return TAV_OK;
 }
 
-// Synchronising tail of a tensor-core search: read the retry flags, redo flagged queries exactly.
-static int resolve_retries(tav_index* ix, const float* d_queries, int n_queries, int k, float min_score,
-                           int64_t item_offset, int64_t* d_items, float* d_scores, int32_t* d_counts,
-                           cudaStream_t s, int* redone) {
-    std::vector<int32_t> host(static_cast<size_t>(n_queries) + 1);
-    int32_t* flags = static_cast<int32_t*>(ix->retry.p);
-    TAV_CUDA(cudaMemcpyAsync(host.data(), flags, static_cast<size_t>(n_queries) * sizeof(int32_t),
-                             cudaMemcpyDeviceToHost, s));
-    TAV_CUDA(cudaMemcpyAsync(&host[n_queries], flags + ix->retry_capacity, sizeof(int32_t),
-                             cudaMemcpyDeviceToHost, s));
-    int out_of_range[2] = {0, 0};  // split form: a corpus / query value beyond the fp16 range
-    if (ix->last_split)
-        TAV_CUDA(cudaMemcpyAsync(out_of_range, ix->split_flag.p, sizeof(out_of_range), cudaMemcpyDeviceToHost, s));
+static inline int32_t* retry_totals(tav_index* ix, int slot) { return static_cast<int32_t*>(ix->retry.p) + 2 * slot; }
+static inline int32_t* retry_flags(tav_index* ix, int slot) {
+    return static_cast<int32_t*>(ix->retry.p) + 2 * kMaxPending + static_cast<size_t>(slot) * ix->retry_cap;
+}
+
+// Synchronising tail of the tensor-core searches: look at the "redo exactly" bookkeeping of every
+// outstanding search and redo flagged queries with the row scan, into that search's own outputs.
+static int finish_pending(tav_index* ix, cudaStream_t s, int* redone) {
+    if (redone) *redone = 0;
+    if (ix->pending.empty()) return TAV_OK;
+    int32_t totals[2 * kMaxPending];
+    int corpus_overflow = 0;
+    TAV_CUDA(cudaMemcpyAsync(totals, ix->retry.p, sizeof(totals), cudaMemcpyDeviceToHost, s));
+    bool any_split = false;
+    for (const Pending& p : ix->pending) any_split |= p.split;
+    if (any_split)
+        TAV_CUDA(cudaMemcpyAsync(&corpus_overflow, ix->split_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     TAV_CUDA(cudaStreamSynchronize(s));
-    ix->pending_queries = 0;
-    const bool redo_all = out_of_range[0] != 0 || out_of_range[1] != 0;
-    const int total = host[n_queries];
-    int n_flagged = 0;
-    for (int q = 0; q < n_queries; ++q) {
-        if (host[q]) ++n_flagged;
-        if (!host[q] && !redo_all) continue;
-        int rc = scan_search(ix, d_queries + static_cast<size_t>(q) * ix->dim, 1, k, min_score, nullptr,
-                             ix->size, item_offset, d_items + static_cast<size_t>(q) * k,
-                             d_scores + static_cast<size_t>(q) * k, d_counts + q, nullptr, s);
-        if (rc != TAV_OK) return rc;
+    std::vector<Pending> todo;
+    todo.swap(ix->pending);
+    ix->next_slot = 0;
+    bool dirty = false;
+    int n_redone = 0;
+    std::vector<int32_t> host;
+    for (const Pending& p : todo) {
+        const int flagged = totals[2 * p.slot], q_overflow = totals[2 * p.slot + 1];
+        const bool redo_all = p.split && (corpus_overflow != 0 || q_overflow != 0);
+        dirty |= flagged != 0 || q_overflow != 0;
+        if (flagged == 0 && !redo_all) continue;
+        host.assign(static_cast<size_t>(p.nq), 1);
+        if (!redo_all) {
+            TAV_CUDA(cudaMemcpyAsync(host.data(), retry_flags(ix, p.slot), static_cast<size_t>(p.nq) * sizeof(int32_t),
+                                     cudaMemcpyDeviceToHost, s));
+            TAV_CUDA(cudaStreamSynchronize(s));
+        }
+        const uint32_t* mask = p.masked ? static_cast<const uint32_t*>(ix->row_mask.p) : nullptr;
+        for (int q = 0; q < p.nq; ++q) {
+            if (!host[q]) continue;
+            ++n_redone;
+            int rc = scan_search(ix, nullptr, false, p.queries + static_cast<size_t>(q) * ix->dim, 1, p.k, p.floor, nullptr,
+                                 ix->size, p.item_offset, p.items + static_cast<size_t>(q) * p.k,
+                                 p.scores + static_cast<size_t>(q) * p.k, p.counts + q, mask, 0, s);
+            if (rc != TAV_OK) return rc;
+        }
     }
-    if (total != 0) TAV_CUDA(cudaMemsetAsync(flags + ix->retry_capacity, 0, sizeof(int32_t), s));
-    if (redone) *redone = redo_all ? n_queries : n_flagged;
-    if (total != n_flagged) {
-        set_error("%d queries of earlier deferred searches needed the exact fallback but were never finished",
-                  total - n_flagged);
-        return TAV_ERR_STATE;
-    }
+    if (dirty) TAV_CUDA(cudaMemsetAsync(ix->retry.p, 0, sizeof(totals), s));
+    if (redone) *redone = n_redone;
     return TAV_OK;
 }
 
 extern "C" {
 
-int tav_finish_search(tav_index* ix, const float* queries_device, int n_queries, int k, float min_score,
-                      int64_t item_offset, int64_t* out_items, float* out_scores, int32_t* out_counts,
-                      void* stream, int* redone) {
-    if (!ix || n_queries < 0) return TAV_ERR_INVALID;
+int tav_finish_search(tav_index* ix, void* stream, int* redone) {
+    if (!ix) return TAV_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ix->mu);
     if (redone) *redone = 0;
-    if (ix->pending_queries == 0) return TAV_OK;  // nothing deferred (row-scan path, or already finished)
-    if (n_queries != ix->pending_queries || !queries_device || !out_items || !out_scores || !out_counts || k < 1) {
-        set_error("tav_finish_search: arguments must repeat the deferred tav_search call");
-        return TAV_ERR_INVALID;
-    }
+    if (ix->pending.empty()) return TAV_OK;  // nothing deferred (row-scan path, or already finished)
     if (int rc = set_device(ix)) return rc;
-    return resolve_retries(ix, queries_device, n_queries, k, min_score, item_offset, out_items, out_scores,
-                           out_counts, static_cast<cudaStream_t>(stream), redone);
+    return finish_pending(ix, static_cast<cudaStream_t>(stream), redone);
 }
 
 int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float min_score,
@@ -574,19 +706,34 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
         return TAV_ERR_INVALID;
     }
     if (n_queries == 0) return TAV_OK;
+    std::lock_guard<std::mutex> lock(ix->mu);
     if (int rc = set_device(ix)) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool q_dev = flags & TAV_QUERIES_ON_DEVICE, o_dev = flags & TAV_OUTPUTS_ON_DEVICE;
     const size_t nk = static_cast<size_t>(n_queries) * k;
+    const uint32_t* d_mask = nullptr;
+    if (flags & TAV_USE_ROW_MASK) {
+        if (ix->row_mask_rows != ix->size || ix->size == 0) {
+            set_error("tav_search: TAV_USE_ROW_MASK without a current row mask (tav_set_row_mask)");
+            return TAV_ERR_STATE;
+        }
+        if (subset) {
+            set_error("tav_search: a row mask and a subset cannot be combined");
+            return TAV_ERR_INVALID;
+        }
+        d_mask = static_cast<const uint32_t*>(ix->row_mask.p);
+    }
+    const int ties_low = (flags & TAV_TIES_LOW_FIRST) ? 1 : 0;
 
     int64_t* d_items = out_items;
     float* d_scores = out_scores;
     int32_t* d_counts = out_counts;
-    // host outputs: results are packed [items | scores | counts] in one device buffer so that a
+    // host outputs: results are packed [items | scores | counts | done word] in one buffer so that a
     // single D2H copy (into pinned staging) brings them back
     const size_t off_scores = nk * sizeof(int64_t);
     const size_t off_counts = off_scores + ((nk * sizeof(float) + 7) & ~size_t(7));
-    const size_t pack_bytes = off_counts + ((static_cast<size_t>(n_queries) * sizeof(int32_t) + 7) & ~size_t(7));
+    const size_t off_done = off_counts + ((static_cast<size_t>(n_queries) * sizeof(int32_t) + 7) & ~size_t(7));
+    const size_t pack_bytes = off_done + 8;
     // Small result sets are written by the kernels straight into the pinned host staging (zero
     // copy over PCIe: no D2H memcpy call on the single-lookup latency path).
     const bool zero_copy_out = !o_dev && pack_bytes <= kZeroCopyOutLimit;
@@ -605,12 +752,16 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
     }
 
     const int64_t n_scan = subset ? subset_len : ix->size;
-    ix->timed_chunks = 0;
-    ix->launches = 0;
-    ix->path = 0;
-    ix->timing_valid = false;
+    TimedSearch* ts = cur_timed(ix);
+    if (!ts) ts = &ix->untimed;
+    const bool timing = ts != &ix->untimed;
+    ts->used = 0;
+    ts->launches = 0;
+    ts->path = 0;
+    ts->valid = false;
 
-    if (n_scan == 0 || ix->size == 0 || ix->dim == 0) {
+    // a NaN min_score admits nothing on every path (`scores >= nan` is all-false in the reference)
+    if (n_scan == 0 || ix->size == 0 || ix->dim == 0 || min_score != min_score) {
         // empty corpus / empty subset: no hits (vectorbase.py:174-175, :214-215)
         if (o_dev) TAV_CUDA(cudaMemsetAsync(d_counts, 0, static_cast<size_t>(n_queries) * sizeof(int32_t), s));
         else memset(out_counts, 0, static_cast<size_t>(n_queries) * sizeof(int32_t));
@@ -621,8 +772,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
         return TAV_ERR_INVALID;
     }
 
-    // subset ordinals: validate on the host (numpy raises IndexError), then upload
-    const int64_t* d_subset = nullptr;
+    // subset ordinals: validate on the host (numpy raises IndexError)
     if (subset) {
         for (int64_t i = 0; i < subset_len; ++i) {
             if (subset[i] < -ix->size || subset[i] >= ix->size) {
@@ -631,6 +781,94 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
                 return TAV_ERR_RANGE;
             }
         }
+    }
+
+    // path choice: tensor cores for batches on 16-bit storage, row scan otherwise
+    bool use_mma = false, use_split = false;
+    const bool mma_able = mma_supported(ix->dtype, ix->dim) || (ix->dtype == TAV_F32 && mma_split_supported(ix->dim));
+    if (!(flags & TAV_FORCE_SCAN) && !subset && mma_able && k <= kPassK && !ties_low) {
+        use_mma = (flags & TAV_FORCE_MMA) || (n_queries >= 16 && ix->size >= 4096);
+        use_split = use_mma && ix->dtype == TAV_F32;
+    }
+    if ((flags & TAV_FORCE_MMA) && !use_mma) {
+        set_error("tav_search: TAV_FORCE_MMA needs dim %% 8 == 0, no subset, k <= %d", kPassK);
+        return TAV_ERR_INVALID;
+    }
+
+    // ---- single-lookup latency form: ONE launch, no copies -------------------------------------
+    // One host query with host outputs on the row-scan path: the query (and a short subset) ride in
+    // the kernel parameters, the last CTA merges and writes the hits into mapped pinned memory and
+    // raises a completion word the host spins on (tools/benchmark_vectorbase.py:97-158 is this call).
+    if (!use_mma && n_queries == 1 && !q_dev && zero_copy_out && !(ix->flags & TAV_NORMALIZE) && k <= 1024 &&
+        scan_max_queries(ix->dim, k) >= 1 && scan1_fits(ix->dim, k, n_scan, subset_len, subset != nullptr) &&
+        !(flags & TAV_NO_FUSED_SCAN)) {
+        ts->path = 1;
+        if (int rc = ensure_scan_counters(ix, s)) return rc;
+        uint64_t* d_bound = static_cast<uint64_t*>(ix->cand_count.p);
+        uint32_t* d_count = reinterpret_cast<uint32_t*>(d_bound + 8);
+        ScanArgs a{};
+        a.corpus = ix->rows;
+        a.dtype = ix->dtype;
+        a.n_corpus = ix->size;
+        a.dim = ix->dim;
+        a.n_scan = n_scan;
+        a.nq = 1;
+        a.floor_score = min_score;
+        a.k = k;
+        a.grid = scan1_grid(ix->device, ix->dim, k, n_scan);
+        a.cand_stride = a.grid * k;
+        TAV_CUDA(ix->cand_keys.ensure(static_cast<size_t>(a.cand_stride) * sizeof(uint64_t)));
+        a.cand_keys = static_cast<uint64_t*>(ix->cand_keys.p);
+        a.cand_count = d_count;
+        a.row_mask = d_mask;
+        a.ties_low = ties_low;
+        a.subset_in_params = subset ? 1 : 0;
+        a.fused = 1;
+        a.fused_ticket = d_count + 8;
+        a.item_offset = item_offset;
+        a.out_items = d_items;
+        a.out_scores = d_scores;
+        a.out_counts = d_counts;
+        volatile uint32_t* done = reinterpret_cast<volatile uint32_t*>(static_cast<char*>(ix->pin_out.p) + off_done);
+        a.done_flag = const_cast<uint32_t*>(done);
+        a.done_seq = ++ix->done_seq;
+        if (a.done_seq == 0) a.done_seq = ++ix->done_seq;
+        *done = 0;
+        if (timing) {
+            TAV_CUDA(ev_record(ts->total[0], s));
+            TAV_CUDA(ev_record(ts->ev[0][0], s));
+        }
+        TAV_CUDA(launch_scan1(a, queries, subset, s));
+        if (timing) {
+            ts->kind[0] = 0;
+            TAV_CUDA(ev_record(ts->ev[0][1], s));
+            ts->used = 1;
+            TAV_CUDA(ev_record(ts->total[1], s));
+        }
+        ts->launches = 1;
+        ts->valid = true;
+        if (timing) ++ix->search_seq;
+        // spin on the completion word (a stream synchronise costs several microseconds more); fall
+        // back to the synchronise when the word does not show up quickly (error, or a busy GPU)
+        bool seen = false;
+        for (int spin = 0; spin < 4000000; ++spin) {
+            if (*done == a.done_seq) {
+                seen = true;
+                break;
+            }
+            if ((spin & 0x3FFF) == 0x3FFF && cudaStreamQuery(s) != cudaErrorNotReady) break;
+        }
+        if (!seen) TAV_CUDA(cudaStreamSynchronize(s));
+        const char* h = static_cast<const char*>(ix->pin_out.p);
+        memcpy(out_items, h, nk * sizeof(int64_t));
+        memcpy(out_scores, h + off_scores, nk * sizeof(float));
+        memcpy(out_counts, h + off_counts, sizeof(int32_t));
+        return TAV_OK;
+    }
+
+    // subset ordinals -> device
+    const int64_t* d_subset = nullptr;
+    if (subset) {
         const size_t sub_bytes = static_cast<size_t>(subset_len) * sizeof(int64_t);
         TAV_CUDA(ix->subset.ensure(sub_bytes));
         const void* src = subset;
@@ -644,7 +882,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
         d_subset = static_cast<const int64_t*>(ix->subset.p);
     }
 
-    if (ix->timing_on) TAV_CUDA(cudaEventRecord(ix->ev_total[0], s));
+    if (timing) TAV_CUDA(ev_record(ts->total[0], s));
 
     // queries -> device float32 (normalised in place when the index is TAV_NORMALIZE)
     const float* d_queries = queries;
@@ -659,7 +897,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
                 src = ix->staging.p;
             }
             TAV_CUDA(launch_convert(src, TAV_F32, ix->queries.p, TAV_F32, n_queries, ix->dim, 1, s));
-            ix->launches += 1;
+            ts->launches += 1;
         } else {
             const void* src = queries;
             if (q_bytes <= kPinnedStageLimit) {
@@ -680,19 +918,8 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
         ix->pin_in_busy = true;
     }
 
-    // path choice: tensor cores for batches on 16-bit storage, row scan otherwise
-    bool use_mma = false, use_split = false;
-    const bool mma_able = mma_supported(ix->dtype, ix->dim) || (ix->dtype == TAV_F32 && mma_split_supported(ix->dim));
-    if (!(flags & TAV_FORCE_SCAN) && !subset && mma_able && k <= kPassK) {
-        use_mma = (flags & TAV_FORCE_MMA) || (n_queries >= 16 && ix->size >= 4096);
-        use_split = use_mma && ix->dtype == TAV_F32;
-    }
-    if ((flags & TAV_FORCE_MMA) && !use_mma) {
-        set_error("tav_search: TAV_FORCE_MMA needs dim %% 8 == 0, no subset, k <= %d", kPassK);
-        return TAV_ERR_INVALID;
-    }
     if (use_split) {
-        const int rc = ensure_split_planes(ix, s);
+        const int rc = ensure_split_planes(ix, ts, s);
         if (rc == TAV_ERR_OOM && !(flags & TAV_FORCE_MMA)) {
             use_mma = use_split = false;  // a speed choice, not a correctness one: the exact row scan serves it
         } else if (rc != TAV_OK) {
@@ -701,70 +928,90 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
     }
 
     if (use_mma) {
-        ix->path = use_split ? 3 : 2;
-        ix->last_split = use_split;
-        MmaArgs m{};
-        m.device = ix->device;
-        m.corpus = use_split ? ix->split_hi.p : ix->rows;
-        m.corpus_lo = use_split ? ix->split_lo.p : nullptr;
-        m.split = use_split ? 1 : 0;
-        m.split_overflow = use_split ? static_cast<int*>(ix->split_flag.p) + 1 : nullptr;
-        if (use_split) TAV_CUDA(cudaMemsetAsync(m.split_overflow, 0, sizeof(int), s));
-        m.dtype = ix->dtype;
-        m.n_corpus = ix->size;
-        m.dim = ix->dim;
-        m.queries = d_queries;
-        m.nq = n_queries;
-        m.floor_score = min_score;
-        m.k = k;
-        m.item_offset = item_offset;
-        m.out_items = d_items;
-        m.out_scores = d_scores;
-        m.out_counts = d_counts;
-        if (n_queries > ix->retry_capacity) {
-            // [flags x capacity | total]; the running total lives right after the flags
-            int32_t carried = 0;
-            if (ix->retry.p)
-                TAV_CUDA(cudaMemcpy(&carried, static_cast<int32_t*>(ix->retry.p) + ix->retry_capacity,
-                                    sizeof(int32_t), cudaMemcpyDeviceToHost));
-            const int cap = std::max(n_queries, 1024);
-            TAV_CUDA(ix->retry.ensure((static_cast<size_t>(cap) + 1) * sizeof(int32_t)));
-            TAV_CUDA(cudaMemcpy(static_cast<int32_t*>(ix->retry.p) + cap, &carried, sizeof(int32_t),
-                                cudaMemcpyHostToDevice));
-            ix->retry_capacity = cap;
+        ts->path = use_split ? 3 : 2;
+        if (n_queries > ix->retry_cap || !ix->retry.p) {
+            if (!ix->pending.empty()) {
+                int redone = 0;
+                if (int rc = finish_pending(ix, s, &redone)) return rc;
+            }
+            const int cap = std::max(std::min(n_queries, kMmaMaxQueries), 1024);
+            const size_t bytes = (static_cast<size_t>(2) * kMaxPending + static_cast<size_t>(kMaxPending) * cap) * sizeof(int32_t);
+            TAV_CUDA(ix->retry.ensure(bytes));
+            TAV_CUDA(cudaMemsetAsync(ix->retry.p, 0, 2 * kMaxPending * sizeof(int32_t), s));
+            ix->retry_cap = cap;
         }
-        m.retry_flags = static_cast<int32_t*>(ix->retry.p);
-        m.retry_total = m.retry_flags + ix->retry_capacity;
-        m.ev = ix->timing_on ? ix->ev_chunk : nullptr;
-        m.ev_kind = ix->ev_kind;
-        m.ev_max = kMaxTimedChunks;
-        int ev_used = 0;
-        m.ev_used = &ev_used;
-        const size_t ws = mma_workspace_bytes(m);
-        TAV_CUDA(ix->mma_ws.ensure(ws));
-        int launches = 0;
-        TAV_CUDA(launch_mma_search(m, ix->mma_ws.p, ws, s, &launches));
-        ix->timed_chunks = ev_used;
-        ix->launches += launches;
+        if (timing)  // the events of this search exist before the launcher records them
+            for (int i = 0; i < kMaxTimedKernels; ++i)
+                for (int j = 0; j < 2; ++j)
+                    if (!ts->ev[i][j]) TAV_CUDA(cudaEventCreate(&ts->ev[i][j]));
+        // one launch sequence per slab of kMmaMaxQueries queries (in practice: one)
+        for (int q0 = 0; q0 < n_queries; q0 += kMmaMaxQueries) {
+            const int nq = std::min(kMmaMaxQueries, n_queries - q0);
+            // bookkeeping slot of this (part of the) search
+            if (static_cast<int>(ix->pending.size()) >= kMaxPending) {
+                int redone = 0;
+                if (int rc = finish_pending(ix, s, &redone)) return rc;
+            }
+            const int slot = ix->next_slot++;
+            MmaArgs m{};
+            m.device = ix->device;
+            m.corpus = use_split ? ix->split_hi.p : ix->rows;
+            m.corpus_lo = use_split ? ix->split_lo.p : nullptr;
+            m.split = use_split ? 1 : 0;
+            m.split_overflow = use_split ? retry_totals(ix, slot) + 1 : nullptr;
+            m.dtype = ix->dtype;
+            m.n_corpus = ix->size;
+            m.dim = ix->dim;
+            m.queries = d_queries + static_cast<size_t>(q0) * ix->dim;
+            m.nq = nq;
+            m.floor_score = min_score;
+            m.k = k;
+            m.item_offset = item_offset;
+            m.out_items = d_items + static_cast<size_t>(q0) * k;
+            m.out_scores = d_scores + static_cast<size_t>(q0) * k;
+            m.out_counts = d_counts + q0;
+            m.retry_flags = retry_flags(ix, slot);
+            m.retry_total = retry_totals(ix, slot);
+            m.row_mask = d_mask;
+            int ev_used = 0;
+            const bool slab_timed = timing && q0 == 0;
+            m.ev = slab_timed ? ts->ev : nullptr;
+            m.ev_kind = ts->kind;
+            m.ev_max = kMaxTimedKernels;
+            m.ev_used = &ev_used;
+            const size_t ws = mma_workspace_bytes(m);
+            if (ws > ix->mma_ws.bytes) {
+                TAV_CUDA(cudaStreamSynchronize(s));  // earlier searches may still use the old workspace
+                TAV_CUDA(ix->mma_ws.ensure(ws));
+                // the sampler's unit counters (start of the workspace) must read zero
+                TAV_CUDA(cudaMemsetAsync(ix->mma_ws.p, 0, std::min<size_t>(ix->mma_ws.bytes, 65536), s));
+            }
+            int launches = 0;
+            TAV_CUDA(launch_mma_search(m, ix->mma_ws.p, ix->mma_ws.bytes, s, &launches));
+            if (slab_timed) ts->used = ev_used;
+            ts->launches += launches;
+            Pending p{m.queries, nq, k, min_score, item_offset, m.out_items, m.out_scores, m.out_counts, slot,
+                      use_split, d_mask != nullptr};
+            ix->pending.push_back(p);
+        }
         // Queries the sampled admission threshold could not settle (fewer than k admitted rows
         // although rows were cut, or candidate overflow) are redone exactly by the row scan —
         // now, or in tav_finish_search when the caller defers the (synchronising) check.
-        if ((flags & TAV_DEFER_RETRY) && o_dev && q_dev) {
-            ix->pending_queries = n_queries;
-        } else {
+        if (!((flags & TAV_DEFER_RETRY) && o_dev && q_dev)) {
             int redone = 0;
-            int rc = resolve_retries(ix, d_queries, n_queries, k, min_score, item_offset, d_items, d_scores,
-                                     d_counts, s, &redone);
-            if (rc != TAV_OK) return rc;
+            if (int rc = finish_pending(ix, s, &redone)) return rc;
         }
     } else {
-        ix->path = 1;
-        int rc = scan_search(ix, d_queries, n_queries, k, min_score, d_subset, n_scan, item_offset,
-                             d_items, d_scores, d_counts, nullptr, s);
+        ts->path = 1;
+        int rc = scan_search(ix, ts, timing, d_queries, n_queries, k, min_score, d_subset, n_scan, item_offset,
+                             d_items, d_scores, d_counts, d_mask, ties_low, s);
         if (rc != TAV_OK) return rc;
     }
-    if (ix->timing_on) TAV_CUDA(cudaEventRecord(ix->ev_total[1], s));
-    ix->timing_valid = true;
+    if (timing) {
+        TAV_CUDA(ev_record(ts->total[1], s));
+        ++ix->search_seq;
+    }
+    ts->valid = true;
 
     if (zero_copy_out) {
         TAV_CUDA(cudaStreamSynchronize(s));
@@ -775,7 +1022,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
     } else if (!o_dev) {
         if (pack_bytes <= kPinnedStageLimit) {
             TAV_CUDA(ix->pin_out.ensure(pack_bytes));
-            TAV_CUDA(cudaMemcpyAsync(ix->pin_out.p, ix->out_pack.p, pack_bytes, cudaMemcpyDeviceToHost, s));
+            TAV_CUDA(cudaMemcpyAsync(ix->pin_out.p, ix->out_pack.p, off_done, cudaMemcpyDeviceToHost, s));
             TAV_CUDA(cudaStreamSynchronize(s));
             const char* h = static_cast<const char*>(ix->pin_out.p);
             memcpy(out_items, h, nk * sizeof(int64_t));
@@ -795,6 +1042,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
 int tav_mma_scores(tav_index* ix, const float* queries, int n_queries, int flags, float* out_device,
                    void* stream) {
     if (!ix || n_queries < 1 || !queries || !out_device) return TAV_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ix->mu);
     const bool split = ix->dtype == TAV_F32;
     if (ix->size == 0 || !(split ? mma_split_supported(ix->dim) : mma_supported(ix->dtype, ix->dim))) {
         set_error("tav_mma_scores: needs a non-empty index with dim %% 8 == 0");
@@ -810,7 +1058,7 @@ int tav_mma_scores(tav_index* ix, const float* queries, int n_queries, int flags
         d_queries = static_cast<const float*>(ix->queries.p);
     }
     if (split)
-        if (int rc = ensure_split_planes(ix, s)) return rc;
+        if (int rc = ensure_split_planes(ix, nullptr, s)) return rc;
     MmaArgs m{};
     m.device = ix->device;
     m.corpus = split ? ix->split_hi.p : ix->rows;
@@ -824,8 +1072,12 @@ int tav_mma_scores(tav_index* ix, const float* queries, int n_queries, int flags
     m.nq = n_queries;
     m.k = 1;
     const size_t ws = mma_workspace_bytes(m);
-    TAV_CUDA(ix->mma_ws.ensure(ws));
-    TAV_CUDA(launch_mma_dump(m, ix->mma_ws.p, ws, out_device, s));
+    if (ws > ix->mma_ws.bytes) {
+        TAV_CUDA(cudaStreamSynchronize(s));
+        TAV_CUDA(ix->mma_ws.ensure(ws));
+        TAV_CUDA(cudaMemsetAsync(ix->mma_ws.p, 0, std::min<size_t>(ix->mma_ws.bytes, 65536), s));
+    }
+    TAV_CUDA(launch_mma_dump(m, ix->mma_ws.p, ix->mma_ws.bytes, out_device, s));
     TAV_CUDA(cudaStreamSynchronize(s));
     return TAV_OK;
 }
@@ -852,58 +1104,114 @@ int tav_merge_topk(int device, int n_lists, int n_queries, int k, const int64_t*
     return TAV_OK;
 }
 
-int tav_set_timing(tav_index* ix, int enabled) {
-    if (!ix) return TAV_ERR_INVALID;
-    ix->timing_on = enabled != 0;
-    ix->timing_valid = false;
+int tav_fold_groups(int device, int n_queries, int k, const int32_t* row_to_group, int64_t n_rows,
+                    int64_t item_offset, int64_t* items, float* scores, int32_t* counts, void* stream) {
+    if (n_queries < 0 || k < 1 || k > 8192 || !row_to_group || n_rows < 0 || !items || !scores || !counts) {
+        set_error("tav_fold_groups: invalid argument (k <= 8192)");
+        return TAV_ERR_INVALID;
+    }
+    if (n_queries == 0) return TAV_OK;
+    TAV_CUDA(cudaSetDevice(device));
+    TAV_CUDA(launch_fold_groups(n_queries, k, row_to_group, n_rows, item_offset, items, scores, counts,
+                                static_cast<cudaStream_t>(stream)));
     return TAV_OK;
 }
 
+int tav_set_timing(tav_index* ix, int enabled) {
+    if (!ix) return TAV_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    ix->timing_on = enabled != 0;
+    if (ix->timing_on && !ix->hist) {
+        ix->hist = new (std::nothrow) TimedSearch[kHistory];
+        if (!ix->hist) return TAV_ERR_OOM;
+        for (int h = 0; h < kHistory; ++h)
+            for (auto& pr : ix->hist[h].ev) pr[0] = pr[1] = nullptr;
+    }
+    ix->search_seq = 0;
+    ix->untimed.valid = false;
+    return TAV_OK;
+}
+
+}  // extern "C"
+
+// sums of one timed search by kernel kind; synchronises on its last event
+static int timed_sums(TimedSearch* t, float* main_ms, float* sample_ms, float* aux_ms, float* total_ms) {
+    TAV_CUDA(cudaEventSynchronize(t->total[1]));
+    float total = 0.0f, sums[3] = {0.0f, 0.0f, 0.0f};
+    TAV_CUDA(cudaEventElapsedTime(&total, t->total[0], t->total[1]));
+    for (int i = 0; i < t->used; ++i) {
+        float ms = 0.0f;
+        TAV_CUDA(cudaEventElapsedTime(&ms, t->ev[i][0], t->ev[i][1]));
+        sums[t->kind[i] >= 0 && t->kind[i] < 3 ? t->kind[i] : 2] += ms;
+    }
+    if (main_ms) *main_ms = sums[0];
+    if (sample_ms) *sample_ms = sums[1];
+    if (aux_ms) *aux_ms = sums[2];
+    if (total_ms) *total_ms = total;
+    return TAV_OK;
+}
+
+extern "C" {
+
 int tav_timing_breakdown(tav_index* ix, float* ms, int* kinds, int capacity, int* n) {
     if (!ix || !n || capacity < 0) return TAV_ERR_INVALID;
-    if (!ix->timing_valid || !ix->timing_on) {
+    std::lock_guard<std::mutex> lock(ix->mu);
+    TimedSearch* t = last_timed(ix);
+    if (!t->valid || !ix->timing_on || t == &ix->untimed) {
         *n = 0;
         return TAV_OK;
     }
     if (int rc = set_device(ix)) return rc;
-    TAV_CUDA(cudaEventSynchronize(ix->ev_total[1]));
-    *n = ix->timed_chunks;
-    for (int i = 0; i < ix->timed_chunks && i < capacity; ++i) {
+    TAV_CUDA(cudaEventSynchronize(t->total[1]));
+    *n = t->used;
+    for (int i = 0; i < t->used && i < capacity; ++i) {
         float v = 0.0f;
-        TAV_CUDA(cudaEventElapsedTime(&v, ix->ev_chunk[i][0], ix->ev_chunk[i][1]));
+        TAV_CUDA(cudaEventElapsedTime(&v, t->ev[i][0], t->ev[i][1]));
         if (ms) ms[i] = v;
-        if (kinds) kinds[i] = ix->ev_kind[i];
+        if (kinds) kinds[i] = t->kind[i];
     }
     return TAV_OK;
 }
 
 int tav_last_timing(tav_index* ix, float* scan_ms, float* total_ms, int* launches, int* path) {
     if (!ix) return TAV_ERR_INVALID;
-    if (!ix->timing_valid) {
-        set_error("tav_last_timing: no timed search on this index yet");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    TimedSearch* t = last_timed(ix);
+    if (!t->valid) {
+        set_error("tav_last_timing: no search on this index yet");
         return TAV_ERR_STATE;
     }
-    if (!ix->timing_on) {  // path / launch count only
+    if (launches) *launches = t->launches;
+    if (path) *path = t->path;
+    if (t == &ix->untimed) {  // path / launch count only
         if (scan_ms) *scan_ms = -1.0f;
         if (total_ms) *total_ms = -1.0f;
-        if (launches) *launches = ix->launches;
-        if (path) *path = ix->path;
         return TAV_OK;
     }
     if (int rc = set_device(ix)) return rc;
-    TAV_CUDA(cudaEventSynchronize(ix->ev_total[1]));
-    float total = 0.0f, scan = 0.0f;
-    TAV_CUDA(cudaEventElapsedTime(&total, ix->ev_total[0], ix->ev_total[1]));
-    for (int i = 0; i < ix->timed_chunks; ++i) {
-        if (ix->ev_kind[i] != 0) continue;
-        float ms = 0.0f;
-        TAV_CUDA(cudaEventElapsedTime(&ms, ix->ev_chunk[i][0], ix->ev_chunk[i][1]));
-        scan += ms;
+    return timed_sums(t, scan_ms, nullptr, nullptr, total_ms);
+}
+
+int tav_timing_history(tav_index* ix, int capacity, float* main_ms, float* sample_ms, float* aux_ms,
+                       float* total_ms, int* n) {
+    if (!ix || !n || capacity < 0) return TAV_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    *n = 0;
+    if (!ix->timing_on || !ix->hist) return TAV_OK;
+    if (int rc = set_device(ix)) return rc;
+    const int64_t have = std::min<int64_t>(ix->search_seq, kHistory);
+    const int64_t take = std::min<int64_t>(have, capacity);
+    for (int64_t i = 0; i < take; ++i) {
+        TimedSearch* t = &ix->hist[(ix->search_seq - take + i) % kHistory];
+        if (!t->valid) continue;
+        float m = 0, sm = 0, ax = 0, tot = 0;
+        if (int rc = timed_sums(t, &m, &sm, &ax, &tot)) return rc;
+        if (main_ms) main_ms[*n] = m;
+        if (sample_ms) sample_ms[*n] = sm;
+        if (aux_ms) aux_ms[*n] = ax;
+        if (total_ms) total_ms[*n] = tot;
+        ++*n;
     }
-    if (scan_ms) *scan_ms = scan;
-    if (total_ms) *total_ms = total;
-    if (launches) *launches = ix->launches;
-    if (path) *path = ix->path;
     return TAV_OK;
 }
 

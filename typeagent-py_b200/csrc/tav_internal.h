@@ -25,7 +25,27 @@ struct ScanArgs {
     int cand_stride;
     uint32_t* cand_count;     // [nq], zero on entry (the select kernel re-zeroes it)
     int grid;                 // CTAs to launch (cand_stride >= grid * k)
+    const uint32_t* row_mask; // optional: bit r set = corpus row r may be returned (predicate pushdown)
+    int ties_low;             // 1: equal scores -> LOWER position first (reference predicate path)
+    // single-launch form (launch_scan1): the last CTA merges all survivors and writes the hits
+    int subset_in_params;     // the subset ordinals travel in the kernel parameters
+    int fused;
+    uint32_t* fused_ticket;   // device counter, zero on entry (self-resetting)
+    int64_t item_offset;
+    int64_t* out_items;       // [nq, k]   (device, or mapped pinned host memory)
+    float* out_scores;
+    int32_t* out_counts;
+    uint32_t* done_flag;      // mapped pinned host word set to done_seq once the hits are written, or nullptr
+    uint32_t done_seq;
 };
+constexpr int kFusedSelectMax = 4096;   // keys the last CTA of the single-launch form sorts at once
+constexpr int kParamQuerySmall = 1024;  // floats of query carried in a 4 KB kernel-parameter blob
+constexpr int kParamQueryBig = 3072;    // ... in the 28 KB blob (with up to kParamSubsetMax ordinals)
+constexpr int kParamSubsetMax = 4096;
+bool scan1_fits(int dim, int k, int64_t n_scan, int64_t subset_len, bool has_subset);
+int scan1_grid(int device, int dim, int k, int64_t n_scan);
+// q_host: float32 [dim] on the host; sub_host: int64 [n_scan] validated ordinals or nullptr
+cudaError_t launch_scan1(const ScanArgs& a, const float* q_host, const int64_t* sub_host, cudaStream_t s);
 int scan_max_queries(int dim, int k);            // how many queries one pass can take (smem)
 int scan_grid(int device, int dtype, int dim, int nq, int k, int64_t n_scan);
 cudaError_t launch_scan(const ScanArgs& a, cudaStream_t s);
@@ -46,8 +66,15 @@ struct SelectArgs {
     int32_t* out_counts;
     uint64_t* bound_out;         // [nq] next-pass bound (last key, 0 if exhausted), or nullptr
     int accumulate;              // counts += n instead of counts = n
+    int ties_low;                // keys carry ~position (see ScanArgs)
 };
 cudaError_t launch_select(const SelectArgs& a, cudaStream_t s);
+
+// in place: hits sorted by score -> first hit of every group (row_to_group[item - item_offset]), the
+// reference's chunk -> message fold (storage/memory/messageindex.py:185-207)
+cudaError_t launch_fold_groups(int n_queries, int k, const int32_t* row_to_group, int64_t n_rows,
+                               int64_t item_offset, int64_t* items, float* scores, int32_t* counts,
+                               cudaStream_t s);
 
 cudaError_t launch_merge(int n_lists, int n_queries, int k, const int64_t* items,
                          const float* scores, const int32_t* counts, int64_t items_stride,
@@ -85,11 +112,13 @@ struct MmaArgs {
     int32_t* out_counts;
     int32_t* retry_flags;  // device [nq]: set to 1 for queries the caller must redo with the row scan
     int32_t* retry_total;  // device [1]: incremented once per flagged query (never reset by the kernels)
+    const uint32_t* row_mask;  // optional device bitmask over corpus rows (bit set = row may be returned)
     cudaEvent_t (*ev)[2];  // optional event pairs, one recorded around every kernel launched
     int* ev_kind;          //   kind per pair: 0 = dominant (MAIN) kernel, 1 = sample pass, 2 = auxiliary
     int ev_max;
     int* ev_used;
 };
+constexpr int kMmaMaxQueries = 32768;  // queries per launch_mma_search call (512 chunks of >= 128 ... callers slab)
 size_t mma_workspace_bytes(const MmaArgs& a);
 cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspace_bytes,
                               cudaStream_t s, int* launches);

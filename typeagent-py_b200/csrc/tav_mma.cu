@@ -9,7 +9,7 @@
 //
 // Shape of one CTA (persistent, one per SM, 320 threads; see the template comment below for the
 // CTA-pair and split-precision forms):
-//   warp 0     TMA producer: per (corpus tile, query block, 64-wide K slice) loads the query
+//   warp 0     TMA producer: per (corpus tile, query chunk, 64-wide K slice) loads the query
 //              slice [128 x 64] and this CTA's corpus slice ([128 x 64] in a pair, [256 x 64]
 //              alone) into a smem ring (6 x 32 KB / 4 x 48 KB, 128-byte swizzle), completing on
 //              an mbarrier.
@@ -25,19 +25,30 @@
 //              (dot, row) pairs into the query's global candidate buffer).  Runs concurrently
 //              with the next tile's MMAs (two TMEM stages).
 //
-// Admission thresholds (k > 8).  A first launch of the same kernel in SAMPLE mode scores a strided
-// sample of corpus tiles and keeps, per thread, its 8 largest dots in registers; a warp-per-query
-// k-way merge takes the 8th largest overall and turns it into a threshold (lowered to the bottom of
-// its float32 score class and never below the caller's min_score) expected to admit max(16k, 512)
-// to 2048 rows of the corpus.  The MAIN launch then streams the whole corpus once; a finalize
-// kernel maps the admitted dots to scores and selects the top k with the library's total order.
+// Work items are (corpus tile, query chunk) pairs — a chunk is 128 queries (single CTA) or 256
+// (CTA pair) — so ANY number of queries is served by ONE launch per pass: the chunks of a tile
+// are visited by neighbouring units at the same time and share the tile through L2, i.e. HBM is
+// read once per search, not once per 256 queries.
+//
+// Admission thresholds.  A first launch of the same kernel in SAMPLE mode scores a strided sample
+// of corpus tiles; its epilogue is branch-free: every thread only keeps the maximum of the 128
+// dots it sees per tile ("block maximum") and stores it.  The CTA that finishes a query chunk's
+// last sample tile then derives, per query, the 8th largest block maximum — at least 8 distinct
+// rows reach it — lowers it to the bottom of its float32 score class, never below the caller's
+// min_score, and publishes it as the admission threshold (expected to admit `target` rows of the
+// corpus, see make_plan).  The MAIN launch then streams the whole corpus once; a finalize kernel
+// maps the admitted dots to scores and selects the top k with the library's total order.
 // Exactness: every row not admitted scores strictly below every admitted row, so if at least k
 // rows were admitted (or the threshold is the caller's min_score itself) the result is the exact
-// top-k.  Queries for which neither holds (pathological score distributions; probability ~6e-8 on
-// well-mixed data) or whose buffer overflowed are flagged and redone by the exact row-scan path.
-// For k <= 8 (REGTOP mode) there is no sampling: the top k live in registers for the whole scan.
+// top-k.  For k <= 8 that always holds (the 8 block maxima are themselves admitted); otherwise a
+// query for which it does not (pathological score distributions; probability ~6e-8 on well-mixed
+// data) or whose buffer overflowed is flagged and redone by the exact row-scan path.
 //
-// Algorithmic bytes per search: N*D*2 (corpus, read once per <=256 queries) + queries + hits.
+// Optional row mask (predicate / post-filter pushdown, reference: aitools/vectorbase.py:191-201,
+// storage/sqlite/messageindex.py:296-326): one bit per corpus row; masked-out rows are dropped
+// in the epilogue (and ignored by the sampler, so the threshold adapts to the mask's density).
+//
+// Algorithmic bytes per search: N*D*2 (corpus, read once) + queries + hits.
 
 #include <float.h>
 #include <math.h>
@@ -56,44 +67,47 @@ constexpr int kBM = 128;   // queries per accumulator  (TMEM lanes)
 constexpr int kBN = 256;   // corpus rows per tile     (TMEM columns per accumulator)
 constexpr int kBK = 64;    // 16-bit elements per K slice = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kStages = 4;
 constexpr int kABytes = kBM * kBK * 2;              // 16 KB
 constexpr int kBBytes = kBN * kBK * 2;              // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;      // 48 KB
 constexpr int kEpiWarps = 8;                        // 4 TMEM lane quadrants x 2 column halves
 constexpr int kMmaThreads = 64 + 32 * kEpiWarps;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kEpiCols = kBN / 2;                   // columns per epilogue warp
-constexpr int kMaxMT = 2;                           // query blocks per launch (2 x 128 queries)
-constexpr int kChunkQueries = kBM * kMaxMT;         // 256
-constexpr int kSampleTop = 8;                        // sampled dots kept per thread (see make_plan)
+constexpr int kSampleTop = 8;                       // the threshold is the 8th largest block maximum
 constexpr int kTmemCols = 512;
-// both forms: 192 KB of tiles + barriers + a 32 KB epilogue scratch (one 32-float column per thread)
-constexpr size_t kScratchBytes = static_cast<size_t>(kEpiWarps) * 32 * 32 * sizeof(float);
-constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(kStages) * kStageBytes + 256 + kScratchBytes;
+constexpr int kMaxChunks = 512;                      // query chunks per launch (tav_search slabs larger batches)
+constexpr int kFinalizeFast = 4096;                 // finalize sorts up to this many candidates in one go
+// both forms: 192 KB of tiles + barriers + a small scratch used by the sampler's tail
+constexpr size_t kScratchBytes = 2 * 128 * kSampleTop * sizeof(float);
+constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(4) * kStageBytes + 256 + kScratchBytes;
 
-enum Mode { kSample = 0, kMain = 1, kDump = 2, kRegTop = 3 };
-constexpr int kRegK = 8;  // REGTOP mode: hits kept per thread in registers (serves k <= 8)
+enum Mode { kSample = 0, kMain = 1, kDump = 2 };
 
 struct KernelArgs {
     int64_t n_rows;
-    int n_work;            // tiles visited by this launch
-    int64_t tile_mul;      // visited tile w -> corpus tile (w * tile_mul) / tile_div
+    int n_tiles_work;      // tiles visited by this launch
+    int64_t tile_mul;      // visited tile t -> corpus tile (t * tile_mul) / tile_div
     int64_t tile_div;
     int kb_count;          // ceil(dim / 64)
-    int nq;                // valid queries in this chunk (<= 256)
-    int mt;                // query blocks (1 or 2)
-    const float* thr;      // MAIN: [256] admission threshold (raw dot) per query
-    float* sample_top;     // SAMPLE: [units, 2 column halves, 256, 16]
-    uint64_t* cand;        // MAIN: [256, capg]  (dot bits << 32 | row)
-    uint32_t* cand_count;  // MAIN: [256]
+    int nq;                // valid queries (all chunks)
+    int nqc;               // query chunks of 128 * CG queries
+    int nq_pad;            // nqc * 128 * CG
+    int chunk_bound;       // 1: unit u serves only chunk u % nqc (SAMPLE); 0: items strided over units
+    float* thr;            // [nq_pad] admission threshold (raw dot) per query: SAMPLE writes, MAIN reads
+    float* floor_x;        // SAMPLE: [nq_pad] the caller's min_score as a dot floor
+    float* sample_max;     // SAMPLE: [n_tiles_work * 2, nq_pad] block maxima
+    uint32_t* sample_done; // SAMPLE: [nqc * CG] finished-unit counters (self-resetting)
+    int32_t* retry;        // SAMPLE: [nq] per-query "redo exactly" flags, cleared here
+    float floor_score;     // SAMPLE: (float)min_score
+    uint64_t* cand;        // MAIN: [nq_pad, capg]  (dot bits << 32 | row)
+    uint32_t* cand_count;  // MAIN: [nq_pad]  (SAMPLE clears it)
     uint32_t capg;
+    const uint32_t* row_mask;  // optional: bit r set = row r may be returned
     float* dump;           // DUMP: [nq, n_rows] raw dots
-    uint64_t* reg_top;     // REGTOP: [units, 2 column halves, 256, kRegK] keys + 1 (0 = empty), descending
-    float floor_score;     // REGTOP: (float)min_score
 };
 
 __device__ __forceinline__ void insert_top(float (&top)[kSampleTop], float x) {
-    // top[] sorted descending; x > top[last] on entry
+    // top[] sorted descending; branch-free insertion (x below top[last] falls out)
 #pragma unroll
     for (int i = 0; i < kSampleTop; ++i) {
         const float hi = fmaxf(top[i], x);
@@ -102,22 +116,50 @@ __device__ __forceinline__ void insert_top(float (&top)[kSampleTop], float x) {
     }
 }
 
-__device__ __forceinline__ void insert_key(uint64_t (&top)[kRegK], uint64_t key) {
-    // top[] sorted descending; key > top[last] on entry
-#pragma unroll
-    for (int i = 0; i < kRegK; ++i) {
-        const uint64_t hi = top[i] > key ? top[i] : key;
-        key = top[i] > key ? key : top[i];
-        top[i] = hi;
+// item i of unit `unit` -> (visited tile t, query chunk c); false when the unit has no such item
+__device__ __forceinline__ bool get_item(const KernelArgs& a, int unit, int n_units, int i, int& t, int& c) {
+    if (a.chunk_bound) {
+        const int upc = n_units / a.nqc;  // units per chunk (the launcher makes n_units a multiple of nqc)
+        c = unit % a.nqc;
+        t = unit / a.nqc + i * upc;
+        return t < a.n_tiles_work;
     }
+    const int64_t w = unit + static_cast<int64_t>(i) * n_units;
+    if (w >= static_cast<int64_t>(a.n_tiles_work) * a.nqc) return false;
+    t = static_cast<int>(w / a.nqc);
+    c = static_cast<int>(w % a.nqc);
+    return true;
 }
 
-// CG = 1: one CTA per tile, up to 2 query blocks processed one after the other.
-// CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per tile: CTA r owns query block r
-//         (its 128 TMEM lanes) and stages rows [128r, 128r+128) of the corpus tile; every MMA is
-//         M=256 x N=256 across the pair, so each CTA's shared memory sees half of the operand
-//         traffic of the single-CTA form — the single-CTA form is smem-bandwidth bound at ~55 %
-//         of the tensor pipe (profiles/README.md).
+// ---- float <-> order-preserving uint32 ------------------------------------------------------
+__device__ __forceinline__ uint32_t float_to_ord(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord_to_float(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
+// smallest dot x whose score clip((x+1)/2,0,1) is >= s: -inf when every x qualifies, +inf when
+// none does (s > 1, or NaN: `score >= NaN` is false for every row, as in the reference)
+__device__ float dot_floor_for_score(float s) {
+    if (s != s) return INFINITY;
+    if (!(s > 0.0f)) return -INFINITY;
+    if (s > 1.0f) return INFINITY;
+    uint32_t lo = float_to_ord(-FLT_MAX), hi = float_to_ord(FLT_MAX);
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (score_from_dot(ord_to_float(mid)) >= s) hi = mid;
+        else lo = mid + 1;
+    }
+    return ord_to_float(lo);
+}
+
+// CG = 1: one CTA per item, 128 queries per chunk.
+// CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per item, 256 queries per chunk: CTA r
+//         owns query block r (its 128 TMEM lanes) and stages rows [128r, 128r+128) of the corpus
+//         tile; every MMA is M=256 x N=256 across the pair, so each CTA's shared memory sees half
+//         of the operand traffic of the single-CTA form — the single-CTA form is smem-bandwidth
+//         bound at ~55 % of the tensor pipe (profiles/README.md).
 // SPLIT: float32 data carried as two fp16 planes, x = hi + lo / 2048 (22 significant bits;
 //         products of fp16 values are exact in the fp32 accumulator).  Three MMAs per K step:
 //         hi.hi' into the MAIN accumulator, hi.lo' + lo.hi' into the CROSS accumulator; the
@@ -135,6 +177,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     constexpr int kStageBytesCta = kPlanes * (kABytes + kBBytesCta);  // [A | B | A_lo | B_lo]
     constexpr int kNumStages = (CG == 2 ? 6 : 4) / kPlanes;  // 192 KB of tiles in every form
     constexpr int kAccStages = SPLIT ? 1 : 2;                // TMEM accumulator stages
+    constexpr int kChunk = kBM * CG;                         // queries per chunk
     extern __shared__ uint8_t smem_dyn[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -144,16 +187,12 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     uint64_t* tfull = bars + 2 * kNumStages;  // [2] MMA -> epilogue      (each CTA its own)
     uint64_t* tempty = tfull + 2;             // [2] epilogue -> MMA      (the leader's copy is used)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    // epilogue scratch [32][kEpiWarps*32]: the insertion-heavy slow paths (SAMPLE, REGTOP) walk a
-    // chunk's 32 values in a ROLLED loop (registers cannot be indexed dynamically; unrolling 32
-    // insertion networks x 8 chunk sites blew the instruction cache: 38 % of epilogue cycles were
-    // instruction-fetch stalls, profiles/README.md).  MAIN's slow path is light and stays unrolled.
-    float* scratch_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    float* scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // sampler tail
+    __shared__ int s_last;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0;
     const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;  // a unit = CTA or CTA pair
-    const int n_mblocks = CG == 2 ? 1 : a.mt;                    // query blocks this CTA walks per tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kNumStages; ++s) {
@@ -186,42 +225,41 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // ================= TMA producer (every CTA) =================
         if (ptx::elect_one()) {
             uint32_t stage = 0, phase = 0;
-            for (int w = unit; w < a.n_work; w += n_units) {
-                const int64_t tile = (static_cast<int64_t>(w) * a.tile_mul) / a.tile_div;
+            int t, c;
+            for (int i = 0; get_item(a, unit, n_units, i, t, c); ++i) {
+                const int64_t tile = (static_cast<int64_t>(t) * a.tile_mul) / a.tile_div;
                 const int32_t row0 = static_cast<int32_t>(tile * kBN + cta_rank * kRowsB);
-                for (int mb = 0; mb < n_mblocks; ++mb) {
-                    const int m = CG == 2 ? static_cast<int>(cta_rank) : mb;
-                    for (int kb = 0; kb < a.kb_count; ++kb) {
-                        ptx::mbar_wait(&empty[stage], phase ^ 1);
-                        uint8_t* sa = tiles + static_cast<size_t>(stage) * kStageBytesCta;
-                        if (CG == 2) {
-                            // Both CTAs' loads complete on the LEADER's barrier; only the leader arms it,
-                            // with the bytes of both (a peer load landing first just drives the pending
-                            // byte count negative until the leader's expect_tx; the peer cannot run a phase
-                            // ahead because its slot is released by the same multicast commit).
-                            const uint32_t lead_full = ptx::map_to_cta(ptx::smem_u32(&full[stage]), 0);
-                            if (cta_rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * kStageBytesCta);
-                            ptx::tma_load_2d_pair(sa, &map_q, lead_full, kb * kBK, m * kBM, ptx::kEvictLast);
-                            ptx::tma_load_2d_pair(sa + kABytes, &map_c, lead_full, kb * kBK, row0, ptx::kEvictFirst);
-                            if (SPLIT) {
-                                uint8_t* sl = sa + kABytes + kBBytesCta;
-                                ptx::tma_load_2d_pair(sl, &map_q_lo, lead_full, kb * kBK, m * kBM, ptx::kEvictLast);
-                                ptx::tma_load_2d_pair(sl + kABytes, &map_c_lo, lead_full, kb * kBK, row0, ptx::kEvictFirst);
-                            }
-                        } else {
-                            ptx::mbar_expect_tx(&full[stage], kStageBytesCta);
-                            ptx::tma_load_2d(sa, &map_q, &full[stage], kb * kBK, m * kBM, ptx::kEvictLast);
-                            ptx::tma_load_2d(sa + kABytes, &map_c, &full[stage], kb * kBK, row0, ptx::kEvictFirst);
-                            if (SPLIT) {
-                                uint8_t* sl = sa + kABytes + kBBytesCta;
-                                ptx::tma_load_2d(sl, &map_q_lo, &full[stage], kb * kBK, m * kBM, ptx::kEvictLast);
-                                ptx::tma_load_2d(sl + kABytes, &map_c_lo, &full[stage], kb * kBK, row0, ptx::kEvictFirst);
-                            }
+                const int32_t qrow = c * kChunk + static_cast<int32_t>(cta_rank) * kBM;
+                for (int kb = 0; kb < a.kb_count; ++kb) {
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = tiles + static_cast<size_t>(stage) * kStageBytesCta;
+                    if (CG == 2) {
+                        // Both CTAs' loads complete on the LEADER's barrier; only the leader arms it,
+                        // with the bytes of both (a peer load landing first just drives the pending
+                        // byte count negative until the leader's expect_tx; the peer cannot run a phase
+                        // ahead because its slot is released by the same multicast commit).
+                        const uint32_t lead_full = ptx::map_to_cta(ptx::smem_u32(&full[stage]), 0);
+                        if (cta_rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * kStageBytesCta);
+                        ptx::tma_load_2d_pair(sa, &map_q, lead_full, kb * kBK, qrow, ptx::kEvictLast);
+                        ptx::tma_load_2d_pair(sa + kABytes, &map_c, lead_full, kb * kBK, row0, ptx::kEvictFirst);
+                        if (SPLIT) {
+                            uint8_t* sl = sa + kABytes + kBBytesCta;
+                            ptx::tma_load_2d_pair(sl, &map_q_lo, lead_full, kb * kBK, qrow, ptx::kEvictLast);
+                            ptx::tma_load_2d_pair(sl + kABytes, &map_c_lo, lead_full, kb * kBK, row0, ptx::kEvictFirst);
                         }
-                        if (++stage == kNumStages) {
-                            stage = 0;
-                            phase ^= 1;
+                    } else {
+                        ptx::mbar_expect_tx(&full[stage], kStageBytesCta);
+                        ptx::tma_load_2d(sa, &map_q, &full[stage], kb * kBK, qrow, ptx::kEvictLast);
+                        ptx::tma_load_2d(sa + kABytes, &map_c, &full[stage], kb * kBK, row0, ptx::kEvictFirst);
+                        if (SPLIT) {
+                            uint8_t* sl = sa + kABytes + kBBytesCta;
+                            ptx::tma_load_2d(sl, &map_q_lo, &full[stage], kb * kBK, qrow, ptx::kEvictLast);
+                            ptx::tma_load_2d(sl + kABytes, &map_c_lo, &full[stage], kb * kBK, row0, ptx::kEvictFirst);
                         }
+                    }
+                    if (++stage == kNumStages) {
+                        stage = 0;
+                        phase ^= 1;
                     }
                 }
             }
@@ -229,217 +267,168 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA of the unit) =================
         if (cta_rank == 0 && ptx::elect_one()) {
-            uint32_t stage = 0, phase = 0, item = 0;
-            for (int w = unit; w < a.n_work; w += n_units) {
-                for (int mb = 0; mb < n_mblocks; ++mb, ++item) {
-                    const uint32_t as = item % kAccStages, aphase = (item / kAccStages) & 1;
-                    ptx::mbar_wait(&tempty[as], aphase ^ 1);  // epilogue(s) drained this accumulator
+            uint32_t stage = 0, phase = 0;
+            int t, c;
+            for (int i = 0; get_item(a, unit, n_units, i, t, c); ++i) {
+                const uint32_t item = static_cast<uint32_t>(i);
+                const uint32_t as = item % kAccStages, aphase = (item / kAccStages) & 1;
+                ptx::mbar_wait(&tempty[as], aphase ^ 1);  // epilogue(s) drained this accumulator
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * kBN;
+                const uint32_t d_cross = tmem_base + kBN;  // SPLIT only
+                for (int kb = 0; kb < a.kb_count; ++kb) {
+                    ptx::mbar_wait(&full[stage], phase);
                     ptx::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + as * kBN;
-                    const uint32_t d_cross = tmem_base + kBN;  // SPLIT only
-                    for (int kb = 0; kb < a.kb_count; ++kb) {
-                        ptx::mbar_wait(&full[stage], phase);
-                        ptx::tc_fence_after();
-                        const uint32_t sa = ptx::smem_u32(tiles + static_cast<size_t>(stage) * kStageBytesCta);
-                        const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
-                        const uint64_t db = ptx::make_kmajor_sw128_desc(sa + kABytes);
+                    const uint32_t sa = ptx::smem_u32(tiles + static_cast<size_t>(stage) * kStageBytesCta);
+                    const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
+                    const uint64_t db = ptx::make_kmajor_sw128_desc(sa + kABytes);
 #pragma unroll
-                        for (int k = 0; k < kBK / kUmmaK; ++k) {
-                            // advance 16 elements = 32 bytes along K inside the swizzle atom
-                            const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
-                            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-                            if (CG == 2) ptx::umma_f16_pair(d_tmem, da + koff, db + koff, idesc, acc);
-                            else ptx::umma_f16(d_tmem, da + koff, db + koff, idesc, acc);
-                            if (SPLIT) {
-                                const uint64_t da_lo = ptx::make_kmajor_sw128_desc(sa + kABytes + kBBytesCta) + koff;
-                                const uint64_t db_lo = ptx::make_kmajor_sw128_desc(sa + 2 * kABytes + kBBytesCta) + koff;
-                                if (CG == 2) {
-                                    ptx::umma_f16_pair(d_cross, da + koff, db_lo, idesc, acc);  // hi . lo'
-                                    ptx::umma_f16_pair(d_cross, da_lo, db + koff, idesc, 1u);   // lo . hi'
-                                } else {
-                                    ptx::umma_f16(d_cross, da + koff, db_lo, idesc, acc);
-                                    ptx::umma_f16(d_cross, da_lo, db + koff, idesc, 1u);
-                                }
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        // advance 16 elements = 32 bytes along K inside the swizzle atom
+                        const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+                        const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                        if (CG == 2) ptx::umma_f16_pair(d_tmem, da + koff, db + koff, idesc, acc);
+                        else ptx::umma_f16(d_tmem, da + koff, db + koff, idesc, acc);
+                        if (SPLIT) {
+                            const uint64_t da_lo = ptx::make_kmajor_sw128_desc(sa + kABytes + kBBytesCta) + koff;
+                            const uint64_t db_lo = ptx::make_kmajor_sw128_desc(sa + 2 * kABytes + kBBytesCta) + koff;
+                            if (CG == 2) {
+                                ptx::umma_f16_pair(d_cross, da + koff, db_lo, idesc, acc);  // hi . lo'
+                                ptx::umma_f16_pair(d_cross, da_lo, db + koff, idesc, 1u);   // lo . hi'
+                            } else {
+                                ptx::umma_f16(d_cross, da + koff, db_lo, idesc, acc);
+                                ptx::umma_f16(d_cross, da_lo, db + koff, idesc, 1u);
                             }
                         }
-                        // smem slot reusable (in both CTAs) once these MMAs retire
-                        if (CG == 2) ptx::umma_commit_pair(&empty[stage], 3);
-                        else ptx::umma_commit(&empty[stage]);
-                        if (++stage == kNumStages) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
                     }
-                    if (CG == 2) ptx::umma_commit_pair(&tfull[as], 3);  // accumulator complete (both CTAs)
-                    else ptx::umma_commit(&tfull[as]);
+                    // smem slot reusable (in both CTAs) once these MMAs retire
+                    if (CG == 2) ptx::umma_commit_pair(&empty[stage], 3);
+                    else ptx::umma_commit(&empty[stage]);
+                    if (++stage == kNumStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
+                if (CG == 2) ptx::umma_commit_pair(&tfull[as], 3);  // accumulator complete (both CTAs)
+                else ptx::umma_commit(&tfull[as]);
             }
         }
     } else {
         // ================= epilogue: one thread = one query (TMEM lane) x half the columns =====
         const int quad = warp & 3;            // TMEM lane quadrant this warp may read
         const int half = (warp - 2) >> 2;     // which 128 of the tile's 256 columns
-        const int lane_q = quad * 32 + lane;
+        const int lane_q = static_cast<int>(cta_rank) * kBM + quad * 32 + lane;  // query inside the chunk
         const uint32_t lead_tempty0 = CG == 2 ? ptx::map_to_cta(ptx::smem_u32(&tempty[0]), 0) : 0;
-        float tau[kMaxMT];
-        float top[kMaxMT][kSampleTop];
-        uint64_t rk[kMaxMT][kRegK];  // REGTOP: best keys (+1) of this thread's columns, descending
-#pragma unroll
-        for (int mb = 0; mb < kMaxMT; ++mb) {
-            const int m = CG == 2 ? static_cast<int>(cta_rank) : mb;
-            const int q = m * kBM + lane_q;
-            tau[mb] = INFINITY;
-            if (MODE == kMain && mb < n_mblocks && q < a.nq) tau[mb] = a.thr[q];
-#pragma unroll
-            for (int i = 0; i < kSampleTop; ++i) top[mb][i] = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < kRegK; ++i) rk[mb][i] = 0;
-        }
-        uint32_t item = 0;
-        for (int w = unit; w < a.n_work; w += n_units) {
-            const int64_t tile = (static_cast<int64_t>(w) * a.tile_mul) / a.tile_div;
+        int t, c;
+        for (int i = 0; get_item(a, unit, n_units, i, t, c); ++i) {
+            const uint32_t item = static_cast<uint32_t>(i);
+            const int64_t tile = (static_cast<int64_t>(t) * a.tile_mul) / a.tile_div;
             const int64_t row0 = tile * kBN + half * kEpiCols;
             // columns of this warp's half that are real corpus rows (warp-uniform)
             const int ncols = static_cast<int>(max(static_cast<int64_t>(0),
                                                    min(static_cast<int64_t>(kEpiCols), a.n_rows - row0)));
-#pragma unroll
-            for (int mb = 0; mb < kMaxMT; ++mb) {
-                if (mb >= n_mblocks) break;
-                const uint32_t as = item % kAccStages, aphase = (item / kAccStages) & 1;
-                ++item;
-                const int m = CG == 2 ? static_cast<int>(cta_rank) : mb;
-                const int q = m * kBM + lane_q;
-                ptx::mbar_wait(&tfull[as], aphase);
-                ptx::tc_fence_after();
-                const uint32_t taddr =
-                    tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * kBN + half * kEpiCols;
+            const uint32_t as = item % kAccStages, aphase = (item / kAccStages) & 1;
+            const int q = c * kChunk + lane_q;  // global query index
+            float tau = INFINITY;
+            if (MODE == kMain && q < a.nq) tau = a.thr[q];
+            float bmax = -INFINITY;             // SAMPLE: best dot of this thread's 128 rows of the tile
+            ptx::mbar_wait(&tfull[as], aphase);
+            ptx::tc_fence_after();
+            const uint32_t taddr =
+                tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * kBN + half * kEpiCols;
 
-                float* scratch = scratch_all + (threadIdx.x - 64);  // element i at scratch[i * 256]
-                auto spill = [&](const uint32_t (&v)[32]) {
+            auto process = [&](const uint32_t (&v)[32], int c0) {
+                const int nvalid = min(32, ncols - c0);  // >= 1 here
+                const uint32_t rbase = static_cast<uint32_t>(row0 + c0);  // a multiple of 32
+                if (MODE == kDump) {
+                    if (q < a.nq) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) scratch[i * (kEpiWarps * 32)] = __uint_as_float(v[i]);
-                };
-                auto process = [&](const uint32_t (&v)[32], int c0) {
-                    const int nvalid = min(32, ncols - c0);  // >= 1 here
-                    if (MODE == kDump) {
-                        if (q < a.nq) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (i < nvalid)
-                                    a.dump[static_cast<size_t>(q) * a.n_rows + row0 + c0 + i] = __uint_as_float(v[i]);
-                        }
-                        return;
+                        for (int i2 = 0; i2 < 32; ++i2)
+                            if (i2 < nvalid)
+                                a.dump[static_cast<size_t>(q) * a.n_rows + row0 + c0 + i2] = __uint_as_float(v[i2]);
                     }
-                    // branch-free screen: the chunk's best dot
-                    float mx = __uint_as_float(v[0]);
+                    return;
+                }
+                if (MODE == kSample) {
+                    // branch-free: sample tiles are full tiles, every column is a real row
+                    if (a.row_mask) {
+                        const uint32_t bits = a.row_mask[rbase >> 5];
 #pragma unroll
-                    for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-                    const uint32_t rbase = static_cast<uint32_t>(row0 + c0);
-                    if (MODE == kMain) {
-                        // Slow path, taken only when the chunk holds an admitted row: branch-free mask of
-                        // the admitted columns, ONE atomicAdd per lane for all of them (the warp's lanes
-                        // issue theirs together: one round trip per chunk instead of one per admitted
-                        // row — the per-row form made the epilogue the bottleneck on small shards, where
-                        // admitted rows are dense; profiles/README.md), then predicated stores.
-                        const float t = tau[mb];
-                        if (mx >= t) {
-                            uint32_t mask = 0;
+                        for (int i2 = 0; i2 < 32; ++i2)
+                            if ((bits >> i2) & 1u) bmax = fmaxf(bmax, __uint_as_float(v[i2]));
+                    } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                mask |= (__uint_as_float(v[i]) >= t && i < nvalid) ? (1u << i) : 0u;
-                            const uint32_t c = __popc(mask);
-                            uint32_t slot = c ? atomicAdd(&a.cand_count[q], c) : 0u;
-                            uint64_t* dst = a.cand + static_cast<size_t>(q) * a.capg;
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                if ((mask >> i) & 1u) {
-                                    if (slot < a.capg) dst[slot] = (static_cast<uint64_t>(v[i]) << 32) | (rbase + i);
-                                    ++slot;
-                                }
-                            }
-                        }
-                    } else if (MODE == kSample) {
-                        if (mx > top[mb][kSampleTop - 1]) {
-                            spill(v);
-#pragma unroll 1
-                            for (int i = 0; i < nvalid; ++i) {
-                                const float x = scratch[i * (kEpiWarps * 32)];
-                                if (x > top[mb][kSampleTop - 1]) insert_top(top[mb], x);
-                            }
-                        }
-                    } else {  // kRegTop: in-register top-k
-                        const float smx = score_from_dot(mx);
-                        if (smx >= a.floor_score && make_key(smx, 0xFFFFFFFFu) >= rk[mb][kRegK - 1]) {
-                            spill(v);
-#pragma unroll 1
-                            for (int i = 0; i < nvalid; ++i) {
-                                const float sc = score_from_dot(scratch[i * (kEpiWarps * 32)]);
-                                const uint64_t key1 = make_key(sc, rbase + i) + 1;
-                                if (sc >= a.floor_score && key1 > rk[mb][kRegK - 1]) insert_key(rk[mb], key1);
-                            }
-                        }
+                        for (int i2 = 0; i2 < 32; ++i2) bmax = fmaxf(bmax, __uint_as_float(v[i2]));
                     }
-                };
-
-                uint32_t va[32], vb[32];
-                if (SPLIT) {
-                    // main and cross accumulators of the same 32 columns, combined: x = main + cross / 2048
-#pragma unroll 1
-                    for (int c0 = 0; c0 < ncols; c0 += 32) {
-                        ptx::tmem_ld_32x32(taddr + c0, va);
-                        ptx::tmem_ld_32x32(taddr + kBN + c0, vb);
-                        ptx::tmem_ld_wait();
+                    return;
+                }
+                // MAIN.  Branch-free screen: the chunk's best dot
+                float mx = __uint_as_float(v[0]);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            va[i] = __float_as_uint(fmaf(__uint_as_float(vb[i]), 1.0f / 2048.0f, __uint_as_float(va[i])));
-                        process(va, c0);
-                    }
-                } else {
-                    // two register buffers: the load of chunk c+1 is in flight while chunk c is screened
-                    if (ncols > 0) {
-                        ptx::tmem_ld_32x32(taddr, va);
-                        ptx::tmem_ld_wait();
-                    }
-#pragma unroll 1
-                    for (int c0 = 0; c0 < kEpiCols; c0 += 64) {
-                        if (c0 + 32 < ncols) ptx::tmem_ld_32x32(taddr + c0 + 32, vb);
-                        if (c0 < ncols) process(va, c0);
-                        ptx::tmem_ld_wait();
-                        if (c0 + 64 < ncols) ptx::tmem_ld_32x32(taddr + c0 + 64, va);
-                        if (c0 + 32 < ncols) process(vb, c0 + 32);
-                        ptx::tmem_ld_wait();
+                for (int i2 = 1; i2 < 32; ++i2) mx = fmaxf(mx, __uint_as_float(v[i2]));
+                // Slow path, taken only when the chunk holds an admitted row: branch-free mask of
+                // the admitted columns, ONE atomicAdd per lane for all of them (the warp's lanes
+                // issue theirs together: one round trip per chunk instead of one per admitted
+                // row — the per-row form made the epilogue the bottleneck on small shards, where
+                // admitted rows are dense; profiles/README.md), then predicated stores.
+                if (mx >= tau) {
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int i2 = 0; i2 < 32; ++i2)
+                        mask |= (__uint_as_float(v[i2]) >= tau && i2 < nvalid) ? (1u << i2) : 0u;
+                    if (a.row_mask) mask &= a.row_mask[rbase >> 5];
+                    const uint32_t cnt = __popc(mask);
+                    uint32_t slot = cnt ? atomicAdd(&a.cand_count[q], cnt) : 0u;
+                    uint64_t* dst = a.cand + static_cast<size_t>(q) * a.capg;
+#pragma unroll
+                    for (int i2 = 0; i2 < 32; ++i2) {
+                        if ((mask >> i2) & 1u) {
+                            if (slot < a.capg) dst[slot] = (static_cast<uint64_t>(v[i2]) << 32) | (rbase + i2);
+                            ++slot;
+                        }
                     }
                 }
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (CG == 2) ptx::mbar_arrive_cluster(lead_tempty0 + as * 8);
-                    else ptx::mbar_arrive(&tempty[as]);
+            };
+
+            uint32_t va[32], vb[32];
+            if (SPLIT) {
+                // main and cross accumulators of the same 32 columns, combined: x = main + cross / 2048
+#pragma unroll 1
+                for (int c0 = 0; c0 < ncols; c0 += 32) {
+                    ptx::tmem_ld_32x32(taddr + c0, va);
+                    ptx::tmem_ld_32x32(taddr + kBN + c0, vb);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i2 = 0; i2 < 32; ++i2)
+                        va[i2] = __float_as_uint(fmaf(__uint_as_float(vb[i2]), 1.0f / 2048.0f, __uint_as_float(va[i2])));
+                    process(va, c0);
+                }
+            } else {
+                // two register buffers: the load of chunk c+1 is in flight while chunk c is screened
+                if (ncols > 0) {
+                    ptx::tmem_ld_32x32(taddr, va);
+                    ptx::tmem_ld_wait();
+                }
+#pragma unroll 1
+                for (int c0 = 0; c0 < kEpiCols; c0 += 64) {
+                    if (c0 + 32 < ncols) ptx::tmem_ld_32x32(taddr + c0 + 32, vb);
+                    if (c0 < ncols) process(va, c0);
+                    ptx::tmem_ld_wait();
+                    if (c0 + 64 < ncols) ptx::tmem_ld_32x32(taddr + c0 + 64, va);
+                    if (c0 + 32 < ncols) process(vb, c0 + 32);
+                    ptx::tmem_ld_wait();
                 }
             }
-        }
-        if (MODE == kSample) {
-#pragma unroll
-            for (int mb = 0; mb < kMaxMT; ++mb) {
-                if (mb >= n_mblocks) break;
-                const int m = CG == 2 ? static_cast<int>(cta_rank) : mb;
-                const int q = m * kBM + lane_q;
-                float* dst = a.sample_top + ((static_cast<size_t>(unit) * 2 + half) * kChunkQueries + q) * kSampleTop;
-#pragma unroll
-                for (int i = 0; i < kSampleTop; ++i) dst[i] = top[mb][i];
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (CG == 2) ptx::mbar_arrive_cluster(lead_tempty0 + as * 8);
+                else ptx::mbar_arrive(&tempty[as]);
             }
+            if (MODE == kSample)
+                a.sample_max[(static_cast<size_t>(t) * 2 + half) * a.nq_pad + q] = bmax;
         }
-        if (MODE == kRegTop) {
-#pragma unroll
-            for (int mb = 0; mb < kMaxMT; ++mb) {
-                if (mb >= n_mblocks) break;
-                const int m = CG == 2 ? static_cast<int>(cta_rank) : mb;
-                const int q = m * kBM + lane_q;
-                uint64_t* dst = a.reg_top + ((static_cast<size_t>(unit) * 2 + half) * kChunkQueries + q) * kRegK;
-#pragma unroll
-                for (int i = 0; i < kRegK; ++i) dst[i] = rk[mb][i];
-            }
-        }
+        if (MODE == kSample) __threadfence();  // block maxima visible device-wide before the unit signs off
     }
 
     // teardown: nobody may leave while the peer still reads its smem / signals its barriers
@@ -451,53 +440,103 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (CG == 2) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
         else ptx::tmem_dealloc(tmem_base, kTmemCols);
     }
-}
 
-// ---- float <-> order-preserving uint32 ------------------------------------------------------
-__device__ __forceinline__ uint32_t float_to_ord(float f) {
-    const uint32_t b = __float_as_uint(f);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float ord_to_float(uint32_t o) {
-    return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
-}
-// smallest dot x whose score clip((x+1)/2,0,1) is >= s: -inf when every x qualifies, +inf when none
-__device__ float dot_floor_for_score(float s) {
-    if (!(s > 0.0f)) return -INFINITY;
-    if (s > 1.0f) return INFINITY;
-    uint32_t lo = float_to_ord(-FLT_MAX), hi = float_to_ord(FLT_MAX);
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (score_from_dot(ord_to_float(mid)) >= s) hi = mid;
-        else lo = mid + 1;
+    if (MODE == kSample) {
+        // ---- sampler tail: the last unit of a query chunk turns block maxima into thresholds ----
+        const int upc = n_units / a.nqc;
+        const int c = unit % a.nqc;
+        const bool has_items = unit / a.nqc < min(upc, a.n_tiles_work);
+        const int n_signing = min(upc, a.n_tiles_work);  // units of this chunk that visited a tile
+        if (threadIdx.x == 0) {
+            int last = 0;
+            if (has_items) {
+                __threadfence();
+                const uint32_t done = atomicAdd(&a.sample_done[c * CG + cta_rank], 1u);
+                last = done == static_cast<uint32_t>(n_signing - 1);
+                if (last) a.sample_done[c * CG + cta_rank] = 0;  // ready for the next search
+            }
+            s_last = last;
+        }
+        __syncthreads();
+        if (s_last && warp >= 2) {
+            __threadfence();
+            const int te = threadIdx.x - 64;          // 0..255
+            const int ql = te & (kBM - 1), part = te >> 7;
+            const int q = c * kChunk + static_cast<int>(cta_rank) * kBM + ql;
+            const int n_blocks = a.n_tiles_work * 2;
+            float top[kSampleTop];
+#pragma unroll
+            for (int i = 0; i < kSampleTop; ++i) top[i] = -INFINITY;
+            for (int b = part; b < n_blocks; b += 2)
+                insert_top(top, __ldcg(&a.sample_max[static_cast<size_t>(b) * a.nq_pad + q]));
+            if (part == 1) {
+#pragma unroll
+                for (int i = 0; i < kSampleTop; ++i) scratch[(i * kBM) + ql] = top[i];
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps
+            if (part == 0) {
+#pragma unroll
+                for (int i = 0; i < kSampleTop; ++i) insert_top(top, scratch[(i * kBM) + ql]);
+                if (q < a.nq) {
+                    const float floor_x = dot_floor_for_score(a.floor_score);
+                    float thr = floor_x;
+                    const float sampled = top[kSampleTop - 1];
+                    if (sampled > -INFINITY) {
+                        // bottom of the float32 score class of the sampled dot: rows below it score strictly less
+                        thr = fmaxf(dot_floor_for_score(score_from_dot(sampled)), floor_x);
+                    }
+                    a.thr[q] = thr;
+                    a.floor_x[q] = floor_x;
+                    a.cand_count[q] = 0;
+                    a.retry[q] = 0;
+                }
+            }
+        }
     }
-    return ord_to_float(lo);
 }
 
+// ---- small kernels around the tensor-core passes ---------------------------------------------
 __device__ __forceinline__ void store_rn(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 __device__ __forceinline__ void store_rn(__half* p, float v) { *p = __float2half_rn(v); }
 
-// queries float32 [nq, dim] -> storage dtype [nq_pad, dim], rows >= nq zeroed
+// per-query state of a search that runs WITHOUT a sample pass (small corpora): the admission
+// threshold is the caller's min_score itself; counters and flags cleared
+__device__ __forceinline__ void init_query_state(int q, int nq, float floor_score, float* thr, float* floor_out,
+                                                 uint32_t* cand_count, int32_t* retry) {
+    if (q >= nq) return;
+    const float floor_x = dot_floor_for_score(floor_score);
+    thr[q] = floor_x;
+    floor_out[q] = floor_x;
+    cand_count[q] = 0;
+    retry[q] = 0;
+}
+
+// queries float32 [nq, dim] -> storage dtype [nq_pad, dim], rows >= nq zeroed; with `init_state`
+// also the per-query search state (see init_query_state) — one launch instead of two
 template <typename T>
-__global__ void query_prep_kernel(const float* q, T* out, int nq, int nq_pad, int dim) {
+__global__ void query_prep_kernel(const float* q, T* out, int nq, int nq_pad, int dim, int init_state,
+                                  float floor_score, float* thr, float* floor_out, uint32_t* cand_count,
+                                  int32_t* retry) {
     const int64_t total = static_cast<int64_t>(nq_pad) * dim;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (int64_t i = tid; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int row = static_cast<int>(i / dim);
         const float v = row < nq ? q[i] : 0.0f;
         store_rn(out + i, v);
     }
+    if (init_state && tid < nq) init_query_state(static_cast<int>(tid), nq, floor_score, thr, floor_out, cand_count, retry);
 }
 
 // float32 x -> fp16 planes hi = fp16(x), lo = fp16((x - hi) * 2048): x ~= hi + lo / 2048 to 2^-22.
 // Rows >= n_valid are zero-filled (query padding).  |x| must be below the fp16 range; a value
 // that is not sets *overflow and the caller redoes the search with the exact row scan.
 __global__ void split_rows_kernel(const float* src, __half* hi, __half* lo, int64_t n_valid, int64_t n_total,
-                                  int dim, int* overflow) {
+                                  int dim, int* overflow, int init_state, float floor_score, float* thr,
+                                  float* floor_out, uint32_t* cand_count, int32_t* retry) {
     const int64_t total = n_total * dim;
+    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     bool bad = false;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    for (int64_t i = tid; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const float x = (i / dim) < n_valid ? src[i] : 0.0f;
         const __half h = __float2half_rn(x);
         const float rest = __fmul_rn(__fsub_rn(x, __half2float(h)), 2048.0f);
@@ -506,126 +545,8 @@ __global__ void split_rows_kernel(const float* src, __half* hi, __half* lo, int6
         bad |= fabsf(x) > 60000.0f;
     }
     if (bad) atomicOr(overflow, 1);
-}
-
-// One WARP per query: the kSampleTop-th largest sampled dot -> admission threshold; also resets
-// the candidate counters.  Every sampling thread left a descending list of its kSampleTop largest
-// dots; the global kSampleTop-th largest is found by popping the largest list head kSampleTop
-// times (warp arg-max over the lanes' lists) — a k-way merge that stops after kSampleTop items.
-__global__ void __launch_bounds__(256)
-threshold_kernel(const float* sample_top, int sample_units, int nq, float floor_score, int use_sample,
-                 float* thr, float* floor_out, uint32_t* cand_count, int32_t* retry) {
-    const int lane = threadIdx.x & 31;
-    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (q >= nq) return;
-    const int n_lists = sample_units * 2;  // two column halves per CTA / CTA pair
-    constexpr int kMaxListsPerLane = 10;   // 148 units x 2 halves / 32 lanes
-    float result = -INFINITY;
-    if (use_sample) {
-        int head[kMaxListsPerLane];
-#pragma unroll
-        for (int j = 0; j < kMaxListsPerLane; ++j) head[j] = 0;
-        for (int round = 0; round < kSampleTop; ++round) {
-            float best = -INFINITY;
-            int best_j = -1;
-#pragma unroll
-            for (int j = 0; j < kMaxListsPerLane; ++j) {
-                const int list = lane + 32 * j;
-                if (list < n_lists && head[j] < kSampleTop) {
-                    const float x = sample_top[(static_cast<size_t>(list) * kChunkQueries + q) * kSampleTop + head[j]];
-                    if (x > best) {
-                        best = x;
-                        best_j = j;
-                    }
-                }
-            }
-            float wbest = best;
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) wbest = fmaxf(wbest, __shfl_xor_sync(0xFFFFFFFFu, wbest, off));
-            const unsigned owners = __ballot_sync(0xFFFFFFFFu, best == wbest && best_j >= 0);
-            if (owners == 0) {  // fewer than kSampleTop finite samples
-                wbest = -INFINITY;
-                result = wbest;
-                break;
-            }
-            if (lane == __ffs(owners) - 1) {
-#pragma unroll
-                for (int j = 0; j < kMaxListsPerLane; ++j)
-                    if (j == best_j) ++head[j];
-            }
-            result = wbest;
-        }
-    }
-    if (lane == 0) {
-        const float floor_x = dot_floor_for_score(floor_score);
-        float t = floor_x;
-        if (use_sample && result > -INFINITY) {
-            // bottom of the float32 score class of the sampled dot: rows below it score strictly less
-            const float snapped = dot_floor_for_score(score_from_dot(result));
-            t = fmaxf(snapped, floor_x);
-        }
-        thr[q] = t;
-        floor_out[q] = floor_x;
-        cand_count[q] = 0;
-        retry[q] = 0;
-    }
-}
-
-// REGTOP merge — one WARP per query: k-way merge of the per-thread descending key lists, stopping
-// after k items; writes the final hits.
-__global__ void __launch_bounds__(256)
-regtop_merge_kernel(const uint64_t* reg_top, int units, int nq, int k, int64_t item_offset, int64_t* out_items,
-                    float* out_scores, int32_t* out_counts, int32_t* retry) {
-    const int lane = threadIdx.x & 31;
-    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (q >= nq) return;
-    const int n_lists = units * 2;
-    constexpr int kMaxListsPerLane = 10;
-    int head[kMaxListsPerLane];
-#pragma unroll
-    for (int j = 0; j < kMaxListsPerLane; ++j) head[j] = 0;
-    int n_out = 0;
-    for (int round = 0; round < k; ++round) {
-        uint64_t best = 0;
-        int best_j = -1;
-#pragma unroll
-        for (int j = 0; j < kMaxListsPerLane; ++j) {
-            const int list = lane + 32 * j;
-            if (list < n_lists && head[j] < kRegK) {
-                const uint64_t key1 = reg_top[(static_cast<size_t>(list) * kChunkQueries + q) * kRegK + head[j]];
-                if (key1 > best) {
-                    best = key1;
-                    best_j = j;
-                }
-            }
-        }
-        uint64_t wbest = best;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, wbest, off);
-            wbest = o > wbest ? o : wbest;
-        }
-        if (wbest == 0) break;  // every list exhausted (keys are stored +1; 0 = empty)
-        if (best == wbest) {    // keys are unique: exactly one lane owns it
-#pragma unroll
-            for (int j = 0; j < kMaxListsPerLane; ++j)
-                if (j == best_j) ++head[j];
-        }
-        if (lane == 0) {
-            const uint64_t key = wbest - 1;
-            out_items[static_cast<size_t>(q) * k + n_out] = static_cast<int64_t>(key_pos(key)) + item_offset;
-            out_scores[static_cast<size_t>(q) * k + n_out] = key_score(key);
-        }
-        ++n_out;
-    }
-    if (lane == 0) {
-        for (int j = n_out; j < k; ++j) {
-            out_items[static_cast<size_t>(q) * k + j] = -1;
-            out_scores[static_cast<size_t>(q) * k + j] = 0.0f;
-        }
-        out_counts[q] = n_out;
-        retry[q] = 0;
-    }
+    if (init_state && tid < n_valid)
+        init_query_state(static_cast<int>(tid), static_cast<int>(n_valid), floor_score, thr, floor_out, cand_count, retry);
 }
 
 // one CTA per query: admitted (dot,row) pairs -> scores -> top-k, or flag the query for the row scan
@@ -638,7 +559,6 @@ finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t capg,
     __shared__ int s_cnt;
     __shared__ uint64_t s_admit;
     const int q = blockIdx.x, tid = threadIdx.x;
-    const int cap = 1 << (32 - __clz(k + kSelectThreads - 1));
     const uint32_t total = cand_count[q];
     const bool overflow = total > capg;
     const bool starved = total < static_cast<uint32_t>(k) && thr[q] > floor_x[q];
@@ -656,30 +576,48 @@ finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t capg,
         }
         return;
     }
-    if (tid == 0) {
-        s_cnt = 0;
-        s_admit = 0;
-    }
-    CandList l{keys, &s_cnt, &s_admit};
     const uint64_t* in = cand + static_cast<size_t>(q) * capg;
-    int need = 0;
-    for (uint32_t base = 0; base < total; base += kSelectThreads) {
-        if (__syncthreads_or(need)) {
-            need = 0;
-            list_compact<kSelectThreads>(l, cap, k, 0);
+    int n;
+    if (total <= static_cast<uint32_t>(kFinalizeFast)) {
+        // the usual case (~`target` admitted rows): everything into shared memory, ONE bitonic sort
+        int cap = 32;
+        while (cap < static_cast<int>(total)) cap <<= 1;
+        for (int i = tid; i < cap; i += kSelectThreads) {
+            uint64_t key = 0;
+            if (i < static_cast<int>(total)) {
+                const uint64_t e = __ldcs(&in[i]);
+                key = make_key(score_from_dot(__uint_as_float(static_cast<uint32_t>(e >> 32))), static_cast<uint32_t>(e));
+            }
+            keys[i] = key;
         }
-        const uint32_t i = base + tid;
-        uint64_t key = 0;
-        if (i < total) {
-            const uint64_t e = in[i];
-            const float x = __uint_as_float(static_cast<uint32_t>(e >> 32));
-            key = make_key(score_from_dot(x), static_cast<uint32_t>(e));
+        bitonic_sort_desc<kSelectThreads>(keys, cap);
+        n = min(static_cast<int>(total), k);
+    } else {
+        const int cap = 1 << (32 - __clz(k + kSelectThreads - 1));
+        if (tid == 0) {
+            s_cnt = 0;
+            s_admit = 0;
         }
-        need |= list_push_warp(l, key, i < total && key >= s_admit, cap - kSelectThreads);
+        CandList l{keys, &s_cnt, &s_admit};
+        int need = 0;
+        for (uint32_t base = 0; base < total; base += kSelectThreads) {
+            if (__syncthreads_or(need)) {
+                need = 0;
+                list_compact<kSelectThreads>(l, cap, k, 0);
+            }
+            const uint32_t i = base + tid;
+            uint64_t key = 0;
+            if (i < total) {
+                const uint64_t e = in[i];
+                const float x = __uint_as_float(static_cast<uint32_t>(e >> 32));
+                key = make_key(score_from_dot(x), static_cast<uint32_t>(e));
+            }
+            need |= list_push_warp(l, key, i < total && key >= s_admit, cap - kSelectThreads);
+        }
+        __syncthreads();
+        list_compact<kSelectThreads>(l, cap, k, 0);
+        n = s_cnt;
     }
-    __syncthreads();
-    list_compact<kSelectThreads>(l, cap, k, 0);
-    const int n = s_cnt;
     for (int j = tid; j < k; j += kSelectThreads) {
         if (j < n) {
             items[j] = static_cast<int64_t>(key_pos(keys[j])) + item_offset;
@@ -726,61 +664,79 @@ bool encode_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int
 
 struct Plan {
     int sms;
+    int cg;            // 1: single CTAs (<= 128 queries), 2: CTA pairs
+    int chunk;         // queries per chunk = 128 * cg
+    int nqc;           // query chunks
+    int nq_pad;        // nqc * chunk
     int n_tiles;
+    int n_full_tiles;
     int kb_count;
     int n_sample;      // tiles in the sample pass (0 = no sampling)
-    int sample_ctas;
-    int main_ctas;
+    int sample_units;  // a multiple of nqc
+    int main_units;
     uint32_t capg;
-    int nq_pad;        // all queries, padded to 128
     // workspace offsets
-    size_t off_q, off_q_lo, off_sample, off_thr, off_floor, off_count, off_cand, total;
-    bool reg_top;      // k <= kRegK: in-register top-k, no sampling / candidate buffers
+    size_t off_q, off_q_lo, off_sample, off_thr, off_floor, off_count, off_done, off_cand, total;
 };
 
 Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
     Plan p{};
     p.sms = 148;
     cudaDeviceGetAttribute(&p.sms, cudaDevAttrMultiProcessorCount, device);
+    p.cg = nq > kBM ? 2 : 1;
+    p.chunk = kBM * p.cg;
+    p.nqc = std::max(1, (nq + p.chunk - 1) / p.chunk);
+    p.nq_pad = p.nqc * p.chunk;
     p.n_tiles = static_cast<int>((n_rows + kBN - 1) / kBN);
+    p.n_full_tiles = static_cast<int>(n_rows / kBN);
     p.kb_count = (dim + kBK - 1) / kBK;
-    p.reg_top = k <= kRegK;
+    const int max_units = p.cg == 2 ? std::max(1, p.sms / 2) : p.sms;
     // Rows we aim to admit per query (`target`).  The threshold is the m-th largest (m = kSampleTop = 8)
-    // of a uniform sample of S = m*N/target rows; the number of corpus rows above it, times S/N, is
-    // ~Gamma(m), so a query starves (< k admitted) with probability P(Gamma(8) < 8k/target): 6e-8 at
-    // target = 16k, but 1e-5 at 8k — one in a hundred thousand query-searches, which one 8-GPU benchmark
-    // run does hit.  Overflow (> 8*target admitted) is rarer still.  Either way the query is merely redone
-    // by the exact row scan.  Large corpora aim at 2048 rows; never fewer than 16k or 512.
-    const int64_t target =
-        std::max<int64_t>(std::max<int64_t>(16ll * k, 512), std::min<int64_t>(2048, n_rows / 4096));
-    if (n_rows <= 16384 || 8 * target >= n_rows) {
+    // block maximum of a uniform sample of L blocks of 128 rows; with p = target / N the chance that a
+    // block's maximum clears the p-quantile is q_b = 1 - (1-p)^128, so L = m / q_b blocks put the m-th
+    // largest block maximum at that quantile.  The number of corpus rows above it is then ~target *
+    // Gamma(m)/m, so a query starves (< k admitted) with probability P(Gamma(8) < 8k/target): 6e-8 at
+    // target = 16k — and never for k <= 8, because the 8 block maxima are 8 distinct admitted rows.
+    // Overflow (> 8*target admitted) is rarer still.  Either way the query is merely redone by the exact
+    // row scan.  Large corpora aim at 2048 rows, small ones at 128; never fewer than 16k.
+    const int64_t target = std::max<int64_t>(
+        16ll * k, std::min<int64_t>(2048, std::max<int64_t>(128, n_rows / 4096)));
+    if (n_rows <= 16384 || 8 * target >= n_rows || p.n_full_tiles < 8) {
         p.n_sample = 0;
         p.capg = static_cast<uint32_t>(n_rows);
     } else {
-        const int64_t sample_rows = (static_cast<int64_t>(kSampleTop) * n_rows + target - 1) / target;
-        p.n_sample = static_cast<int>(std::min<int64_t>(p.n_tiles, std::max<int64_t>(1, (sample_rows + kBN - 1) / kBN)));
+        const double prob = static_cast<double>(target) / static_cast<double>(n_rows);
+        const double q_b = 1.0 - pow(1.0 - prob, 128.0);
+        const int64_t blocks = static_cast<int64_t>(ceil(kSampleTop / q_b));
+        p.n_sample = static_cast<int>(std::min<int64_t>(p.n_full_tiles, std::max<int64_t>(4, (blocks + 1) / 2)));
         p.capg = static_cast<uint32_t>(8 * target);
     }
-    p.sample_ctas = std::max(1, std::min(p.n_sample, p.sms));
-    p.main_ctas = std::min(p.n_tiles, p.sms);
-    p.nq_pad = ((nq + kBM - 1) / kBM) * kBM;
+    // sample units: chunk-bound (unit u serves chunk u % nqc), so a multiple of nqc
+    {
+        const int per_chunk = std::max(1, std::min(std::max(1, max_units / p.nqc), std::max(1, p.n_sample)));
+        p.sample_units = per_chunk * p.nqc;  // may exceed max_units when nqc > max_units: extra units queue
+    }
+    p.main_units = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(p.n_tiles) * p.nqc, max_units));
     auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
+    // the sampler's self-resetting unit counters live at a FIXED place (offset 0), whatever the shape of
+    // the search: they must read zero at the start of every search and only the kernels ever write them
     size_t off = 0;
+    p.off_done = off;
+    off = align(off + static_cast<size_t>(kMaxChunks) * 2 * sizeof(uint32_t));
     p.off_q = off;
     off = align(off + static_cast<size_t>(p.nq_pad) * dim * 2);
     p.off_q_lo = off;  // lo plane of the queries (split form only; reserved always)
     off = align(off + static_cast<size_t>(p.nq_pad) * dim * 2);
-    p.off_sample = off;  // SAMPLE lists (float x kSampleTop) or REGTOP lists (u64 x kRegK), per unit and half
-    off = align(off + static_cast<size_t>(std::max(p.sample_ctas, p.reg_top ? p.main_ctas : 0)) * 2 * kChunkQueries *
-                          std::max(kSampleTop * sizeof(float), kRegK * sizeof(uint64_t)));
+    p.off_sample = off;  // block maxima [n_sample * 2, nq_pad]
+    off = align(off + static_cast<size_t>(std::max(1, p.n_sample)) * 2 * p.nq_pad * sizeof(float));
     p.off_thr = off;
-    off = align(off + kChunkQueries * sizeof(float));
+    off = align(off + static_cast<size_t>(p.nq_pad) * sizeof(float));
     p.off_floor = off;
-    off = align(off + kChunkQueries * sizeof(float));
+    off = align(off + static_cast<size_t>(p.nq_pad) * sizeof(float));
     p.off_count = off;
-    off = align(off + kChunkQueries * sizeof(uint32_t));
+    off = align(off + static_cast<size_t>(p.nq_pad) * sizeof(uint32_t));
     p.off_cand = off;
-    off = align(off + (p.reg_top ? 0 : static_cast<size_t>(kChunkQueries) * p.capg * sizeof(uint64_t)));
+    off = align(off + static_cast<size_t>(p.nq_pad) * p.capg * sizeof(uint64_t));
     p.total = off;
     return p;
 }
@@ -813,31 +769,38 @@ cudaError_t launch_kernel_cg(const Maps& m, const KernelArgs& ka, uint32_t idesc
     return cudaLaunchKernelEx(&cfg, kern, m.q, m.c1, m.q_lo, m.c1_lo, ka, idesc);
 }
 
-// mt == 2 (129..256 queries): CTA pairs; mt == 1: single CTAs; split: two-plane fp16 (float32 data)
+// cg == 2 (more than 128 queries): CTA pairs; cg == 1: single CTAs; split: two-plane fp16 (float32 data)
 template <int MODE>
-cudaError_t launch_kernel(const Maps& m, const KernelArgs& ka, int dtype, bool split, int units, cudaStream_t s) {
+cudaError_t launch_kernel(const Maps& m, const KernelArgs& ka, int cg, int dtype, bool split, int units,
+                          cudaStream_t s) {
     const int fmt = dtype == TAV_BF16 ? 1 : 0;
-    const uint32_t idesc = ptx::make_idesc_f16(ka.mt == 2 ? 2 * kBM : kBM, kBN, fmt);
-    if (ka.mt == 2)
+    const uint32_t idesc = ptx::make_idesc_f16(cg * kBM, kBN, fmt);
+    if (cg == 2)
         return split ? launch_kernel_cg<MODE, 2, true>(m, ka, idesc, units, s)
                      : launch_kernel_cg<MODE, 2, false>(m, ka, idesc, units, s);
     return split ? launch_kernel_cg<MODE, 1, true>(m, ka, idesc, units, s)
                  : launch_kernel_cg<MODE, 1, false>(m, ka, idesc, units, s);
 }
 
-cudaError_t prep_queries(const MmaArgs& a, void* dst, void* dst_lo, int nq_pad, cudaStream_t s) {
+cudaError_t prep_queries(const MmaArgs& a, void* dst, void* dst_lo, int nq_pad, int init_state, float* thr,
+                         float* floor_out, uint32_t* cand_count, cudaStream_t s) {
     const int64_t total = static_cast<int64_t>(nq_pad) * a.dim;
-    const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 8));
+    const int grid = static_cast<int>(std::max<int64_t>(
+        std::min<int64_t>((total + 255) / 256, 148 * 8), init_state ? (a.nq + 255) / 256 : 1));
     if (a.split) {
         split_rows_kernel<<<grid, 256, 0, s>>>(a.queries, static_cast<__half*>(dst), static_cast<__half*>(dst_lo),
-                                               a.nq, nq_pad, a.dim, a.split_overflow);
+                                               a.nq, nq_pad, a.dim, a.split_overflow, init_state, a.floor_score, thr,
+                                               floor_out, cand_count, a.retry_flags);
         return cudaGetLastError();
     }
     if (a.dtype == TAV_BF16)
-        query_prep_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(a.queries, static_cast<__nv_bfloat16*>(dst), a.nq,
-                                                              nq_pad, a.dim);
+        query_prep_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(a.queries, static_cast<__nv_bfloat16*>(dst), a.nq, nq_pad,
+                                                              a.dim, init_state, a.floor_score, thr, floor_out,
+                                                              cand_count, a.retry_flags);
     else
-        query_prep_kernel<__half><<<grid, 256, 0, s>>>(a.queries, static_cast<__half*>(dst), a.nq, nq_pad, a.dim);
+        query_prep_kernel<__half><<<grid, 256, 0, s>>>(a.queries, static_cast<__half*>(dst), a.nq, nq_pad, a.dim,
+                                                       init_state, a.floor_score, thr, floor_out, cand_count,
+                                                       a.retry_flags);
     return cudaGetLastError();
 }
 
@@ -853,7 +816,8 @@ cudaError_t launch_split_rows(const float* src, void* hi, void* lo, int64_t n, i
     if (n == 0) return cudaSuccess;
     const int64_t total = n * dim;
     const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));
-    split_rows_kernel<<<grid, 256, 0, s>>>(src, static_cast<__half*>(hi), static_cast<__half*>(lo), n, n, dim, overflow);
+    split_rows_kernel<<<grid, 256, 0, s>>>(src, static_cast<__half*>(hi), static_cast<__half*>(lo), n, n, dim, overflow,
+                                           0, 0.0f, nullptr, nullptr, nullptr, nullptr);
     return cudaGetLastError();
 }
 
@@ -861,20 +825,15 @@ namespace {
 // storage dtype the tensor-core kernel sees: fp16 planes for split float32 data
 inline int mma_dtype(const MmaArgs& a) { return a.split ? TAV_F16 : a.dtype; }
 
-bool build_corpus_maps(const MmaArgs& a, Maps& m) {
+bool build_maps(const MmaArgs& a, const void* d_q, const void* d_q_lo, int nq_pad, Maps& m) {
     const int dt = mma_dtype(a);
     if (!encode_map(&m.c1, dt, a.corpus, a.n_corpus, a.dim, kBN)) return false;
     if (!encode_map(&m.c2, dt, a.corpus, a.n_corpus, a.dim, kBN / 2)) return false;
     const void* lo = a.split ? a.corpus_lo : a.corpus;  // unused maps still need a valid encoding
     if (!encode_map(&m.c1_lo, dt, lo, a.n_corpus, a.dim, kBN)) return false;
-    return encode_map(&m.c2_lo, dt, lo, a.n_corpus, a.dim, kBN / 2);
-}
-bool build_query_maps(const MmaArgs& a, const void* d_q, const void* d_q_lo, int q0, int mt, Maps& m) {
-    const int dt = mma_dtype(a);
-    const size_t off = static_cast<size_t>(q0) * a.dim * 2;
-    if (!encode_map(&m.q, dt, static_cast<const char*>(d_q) + off, mt * kBM, a.dim, kBM)) return false;
-    const void* lo = a.split ? d_q_lo : d_q;
-    return encode_map(&m.q_lo, dt, static_cast<const char*>(lo) + off, mt * kBM, a.dim, kBM);
+    if (!encode_map(&m.c2_lo, dt, lo, a.n_corpus, a.dim, kBN / 2)) return false;
+    if (!encode_map(&m.q, dt, d_q, nq_pad, a.dim, kBM)) return false;
+    return encode_map(&m.q_lo, dt, a.split ? d_q_lo : d_q, nq_pad, a.dim, kBM);
 }
 bool args_ok(const MmaArgs& a) {
     if (a.n_corpus >= (1ll << 31) || reinterpret_cast<uintptr_t>(a.corpus) % 16 != 0) return false;
@@ -887,7 +846,7 @@ size_t mma_workspace_bytes(const MmaArgs& a) { return make_plan(a.device, a.n_co
 
 cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s,
                               int* launches) {
-    if (!args_ok(a) || a.k > kPassK) return cudaErrorInvalidValue;
+    if (!args_ok(a) || a.k > kPassK || a.nq < 1 || a.nq > kMmaMaxQueries) return cudaErrorInvalidValue;
     const Plan p = make_plan(a.device, a.n_corpus, a.dim, a.nq, a.k);
     if (workspace_bytes < p.total) return cudaErrorInvalidValue;
     char* ws = static_cast<char*>(workspace);
@@ -897,107 +856,84 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
     float* d_thr = reinterpret_cast<float*>(ws + p.off_thr);
     float* d_floor = reinterpret_cast<float*>(ws + p.off_floor);
     uint32_t* d_count = reinterpret_cast<uint32_t*>(ws + p.off_count);
+    uint32_t* d_done = reinterpret_cast<uint32_t*>(ws + p.off_done);
     uint64_t* d_cand = reinterpret_cast<uint64_t*>(ws + p.off_cand);
-    int n_launch = 0;
+    int n_launch = 0, ev_used = 0;
+    cudaError_t e;
+    auto ev_begin = [&]() -> cudaError_t {
+        return (a.ev && ev_used < a.ev_max) ? cudaEventRecord(a.ev[ev_used][0], s) : cudaSuccess;
+    };
+    auto ev_end = [&](int kind) -> cudaError_t {
+        if (!(a.ev && ev_used < a.ev_max)) return cudaSuccess;
+        if (a.ev_kind) a.ev_kind[ev_used] = kind;
+        return cudaEventRecord(a.ev[ev_used++][1], s);
+    };
 
-    cudaError_t e = prep_queries(a, d_q, d_q_lo, p.nq_pad, s);
+    // queries -> storage dtype; without a sample pass this launch also initialises thresholds / counters
+    if ((e = ev_begin()) != cudaSuccess) return e;
+    e = prep_queries(a, d_q, d_q_lo, p.nq_pad, p.n_sample == 0 ? 1 : 0, d_thr, d_floor, d_count, s);
     if (e != cudaSuccess) return e;
+    if ((e = ev_end(2)) != cudaSuccess) return e;
     ++n_launch;
 
     Maps maps;
-    if (!build_corpus_maps(a, maps)) return cudaErrorUnknown;
+    if (!build_maps(a, d_q, d_q_lo, p.nq_pad, maps)) return cudaErrorUnknown;
     const int kdt = mma_dtype(a);
     const bool split = a.split != 0;
 
-    int ev_used = 0;
-    for (int q0 = 0; q0 < a.nq; q0 += kChunkQueries) {
-        const int nq = std::min(kChunkQueries, a.nq - q0);
-        const int mt = (nq + kBM - 1) / kBM;
-        if (!build_query_maps(a, d_q, d_q_lo, q0, mt, maps)) return cudaErrorUnknown;
+    KernelArgs ka{};
+    ka.n_rows = a.n_corpus;
+    ka.kb_count = p.kb_count;
+    ka.nq = a.nq;
+    ka.nqc = p.nqc;
+    ka.nq_pad = p.nq_pad;
+    ka.thr = d_thr;
+    ka.floor_x = d_floor;
+    ka.sample_max = d_sample;
+    ka.sample_done = d_done;
+    ka.retry = a.retry_flags;
+    ka.floor_score = a.floor_score;
+    ka.cand = d_cand;
+    ka.cand_count = d_count;
+    ka.capg = p.capg;
+    ka.row_mask = a.row_mask;
 
-        KernelArgs ka{};
-        ka.n_rows = a.n_corpus;
-        ka.kb_count = p.kb_count;
-        ka.nq = nq;
-        ka.mt = mt;
-        ka.thr = d_thr;
-        ka.sample_top = d_sample;
-        ka.cand = d_cand;
-        ka.cand_count = d_count;
-        ka.capg = p.capg;
-        const int max_units = mt == 2 ? std::max(1, p.sms / 2) : p.sms;
-        const int sample_units = std::max(1, std::min(std::min(p.n_sample, max_units), 160));  // <= 320 lists
-        const int main_units = std::min(p.n_tiles, max_units);
-
-        auto ev_begin = [&]() -> cudaError_t {
-            return (a.ev && ev_used < a.ev_max) ? cudaEventRecord(a.ev[ev_used][0], s) : cudaSuccess;
-        };
-        auto ev_end = [&](int kind) -> cudaError_t {
-            if (!(a.ev && ev_used < a.ev_max)) return cudaSuccess;
-            if (a.ev_kind) a.ev_kind[ev_used] = kind;
-            return cudaEventRecord(a.ev[ev_used++][1], s);
-        };
-        if (p.reg_top) {
-            // k <= 8: top-k kept in registers across the whole corpus, then a warp-per-query merge
-            ka.n_work = p.n_tiles;
-            ka.tile_mul = 1;
-            ka.tile_div = 1;
-            ka.reg_top = reinterpret_cast<uint64_t*>(d_sample);
-            ka.floor_score = a.floor_score;
-            if ((e = ev_begin()) != cudaSuccess) return e;
-            e = launch_kernel<kRegTop>(maps, ka, kdt, split, std::min(main_units, 160), s);
-            if (e != cudaSuccess) return e;
-            if ((e = ev_end(0)) != cudaSuccess) return e;
-            ++n_launch;
-            if ((e = ev_begin()) != cudaSuccess) return e;
-            regtop_merge_kernel<<<(nq + 7) / 8, 256, 0, s>>>(
-                ka.reg_top, std::min(main_units, 160), nq, a.k, a.item_offset,
-                a.out_items + static_cast<size_t>(q0) * a.k, a.out_scores + static_cast<size_t>(q0) * a.k,
-                a.out_counts + q0, a.retry_flags + q0);
-            if ((e = cudaGetLastError()) != cudaSuccess) return e;
-            if ((e = ev_end(2)) != cudaSuccess) return e;
-            ++n_launch;
-            continue;
-        }
-        if (p.n_sample > 0) {
-            ka.n_work = p.n_sample;
-            ka.tile_mul = p.n_tiles;
-            ka.tile_div = p.n_sample;
-            if ((e = ev_begin()) != cudaSuccess) return e;
-            e = launch_kernel<kSample>(maps, ka, kdt, split, sample_units, s);
-            if (e != cudaSuccess) return e;
-            if ((e = ev_end(1)) != cudaSuccess) return e;
-            ++n_launch;
-        }
+    if (p.n_sample > 0) {
+        // strided sample of FULL tiles; the last unit of every query chunk publishes the thresholds
+        ka.n_tiles_work = p.n_sample;
+        ka.tile_mul = p.n_full_tiles;
+        ka.tile_div = p.n_sample;
+        ka.chunk_bound = 1;
         if ((e = ev_begin()) != cudaSuccess) return e;
-        threshold_kernel<<<(nq + 7) / 8, 256, 0, s>>>(d_sample, sample_units, nq, a.floor_score,
-                                                      p.n_sample > 0 ? 1 : 0, d_thr, d_floor, d_count,
-                                                      a.retry_flags + q0);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if ((e = ev_end(2)) != cudaSuccess) return e;
-        ++n_launch;
-
-        ka.n_work = p.n_tiles;
-        ka.tile_mul = 1;
-        ka.tile_div = 1;
-        if ((e = ev_begin()) != cudaSuccess) return e;
-        e = launch_kernel<kMain>(maps, ka, kdt, split, main_units, s);
+        e = launch_kernel<kSample>(maps, ka, p.cg, kdt, split, p.sample_units, s);
         if (e != cudaSuccess) return e;
-        if ((e = ev_end(0)) != cudaSuccess) return e;
-        ++n_launch;
-
-        const size_t sel_smem = static_cast<size_t>(next_pow2(a.k + kSelectThreads)) * sizeof(uint64_t);
-        static int finalize_granted[16] = {};
-        e = ensure_dynamic_smem(finalize_kernel, sel_smem, finalize_granted);
-        if (e != cudaSuccess) return e;
-        if ((e = ev_begin()) != cudaSuccess) return e;
-        finalize_kernel<<<nq, kSelectThreads, sel_smem, s>>>(
-            d_cand, d_count, p.capg, d_thr, d_floor, a.k, a.item_offset, a.out_items + static_cast<size_t>(q0) * a.k,
-            a.out_scores + static_cast<size_t>(q0) * a.k, a.out_counts + q0, a.retry_flags + q0, a.retry_total);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if ((e = ev_end(2)) != cudaSuccess) return e;
+        if ((e = ev_end(1)) != cudaSuccess) return e;
         ++n_launch;
     }
+
+    ka.n_tiles_work = p.n_tiles;
+    ka.tile_mul = 1;
+    ka.tile_div = 1;
+    ka.chunk_bound = 0;
+    if ((e = ev_begin()) != cudaSuccess) return e;
+    e = launch_kernel<kMain>(maps, ka, p.cg, kdt, split, p.main_units, s);
+    if (e != cudaSuccess) return e;
+    if ((e = ev_end(0)) != cudaSuccess) return e;
+    ++n_launch;
+
+    const size_t sel_smem =
+        static_cast<size_t>(std::max(kFinalizeFast, next_pow2(a.k + kSelectThreads))) * sizeof(uint64_t);
+    static int finalize_granted[16] = {};
+    e = ensure_dynamic_smem(finalize_kernel, sel_smem, finalize_granted);
+    if (e != cudaSuccess) return e;
+    if ((e = ev_begin()) != cudaSuccess) return e;
+    finalize_kernel<<<a.nq, kSelectThreads, sel_smem, s>>>(d_cand, d_count, p.capg, d_thr, d_floor, a.k, a.item_offset,
+                                                           a.out_items, a.out_scores, a.out_counts, a.retry_flags,
+                                                           a.retry_total);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = ev_end(2)) != cudaSuccess) return e;
+    ++n_launch;
+
     if (launches) *launches = n_launch;
     if (a.ev_used) *a.ev_used = ev_used;
     return cudaSuccess;
@@ -1005,34 +941,27 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
 
 // Debug / verification entry: all raw dot products of the tensor-core path, out[nq, n_rows] (device).
 cudaError_t launch_mma_dump(const MmaArgs& a, void* workspace, size_t workspace_bytes, float* out, cudaStream_t s) {
-    if (!args_ok(a)) return cudaErrorInvalidValue;
+    if (!args_ok(a) || a.nq < 1 || a.nq > kMmaMaxQueries) return cudaErrorInvalidValue;
     const Plan p = make_plan(a.device, a.n_corpus, a.dim, a.nq, 1);
     if (workspace_bytes < p.total) return cudaErrorInvalidValue;
     char* ws = static_cast<char*>(workspace);
     void* d_q = ws + p.off_q;
     void* d_q_lo = ws + p.off_q_lo;
-    cudaError_t e = prep_queries(a, d_q, d_q_lo, p.nq_pad, s);
+    cudaError_t e = prep_queries(a, d_q, d_q_lo, p.nq_pad, 0, nullptr, nullptr, nullptr, s);
     if (e != cudaSuccess) return e;
     Maps maps;
-    if (!build_corpus_maps(a, maps)) return cudaErrorUnknown;
-    for (int q0 = 0; q0 < a.nq; q0 += kChunkQueries) {
-        const int nq = std::min(kChunkQueries, a.nq - q0);
-        const int mt = (nq + kBM - 1) / kBM;
-        if (!build_query_maps(a, d_q, d_q_lo, q0, mt, maps)) return cudaErrorUnknown;
-        KernelArgs ka{};
-        ka.n_rows = a.n_corpus;
-        ka.kb_count = p.kb_count;
-        ka.nq = nq;
-        ka.mt = mt;
-        ka.n_work = p.n_tiles;
-        ka.tile_mul = 1;
-        ka.tile_div = 1;
-        ka.dump = out + static_cast<size_t>(q0) * a.n_corpus;
-        const int max_units = mt == 2 ? std::max(1, p.sms / 2) : p.sms;
-        e = launch_kernel<kDump>(maps, ka, mma_dtype(a), a.split != 0, std::min(p.n_tiles, max_units), s);
-        if (e != cudaSuccess) return e;
-    }
-    return cudaSuccess;
+    if (!build_maps(a, d_q, d_q_lo, p.nq_pad, maps)) return cudaErrorUnknown;
+    KernelArgs ka{};
+    ka.n_rows = a.n_corpus;
+    ka.kb_count = p.kb_count;
+    ka.nq = a.nq;
+    ka.nqc = p.nqc;
+    ka.nq_pad = p.nq_pad;
+    ka.n_tiles_work = p.n_tiles;
+    ka.tile_mul = 1;
+    ka.tile_div = 1;
+    ka.dump = out;
+    return launch_kernel<kDump>(maps, ka, p.cg, mma_dtype(a), a.split != 0, p.main_units, s);
 }
 
 }  // namespace tav

@@ -15,6 +15,9 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
 
 #include "tav_common.cuh"
 #include "tav_internal.h"
@@ -30,9 +33,11 @@ static inline int scan_cap(int k) {
     if (c < 128) c = 128;  // >= k + kRoundRows always
     return c;
 }
-static inline size_t scan_smem_bytes(int qb, int dim, int k) {
+static inline size_t scan_smem_bytes(int qb, int dim, int k, bool fused = false) {
     size_t q_bytes = (static_cast<size_t>(qb) * dim * sizeof(float) + 15) & ~size_t(15);
-    return q_bytes + static_cast<size_t>(qb) * scan_cap(k) * sizeof(uint64_t);
+    size_t lists = static_cast<size_t>(qb) * scan_cap(k) * sizeof(uint64_t);
+    if (fused) lists = std::max(lists, static_cast<size_t>(kFusedSelectMax) * sizeof(uint64_t));
+    return q_bytes + lists;
 }
 
 int scan_max_queries(int dim, int k) {
@@ -104,8 +109,32 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&v)[NV], int lane) 
     }
 }
 
-template <typename T, int QB, bool VEC>
-__global__ void __launch_bounds__(kScanThreads) scan_rows_kernel(const ScanArgs a) {
+// Single-lookup latency form (BLOB != NoBlob): the query vector — and a short subset — travel as
+// KERNEL PARAMETERS (no H2D copy, no staging buffer: the launch itself carries them), and the CTA
+// that finishes last merges every CTA's survivors and writes the hits (no second launch).
+struct NoBlob {
+    float q[1];
+    int32_t sub[1];
+};
+template <int QN, int SN>
+struct ParamBlob {
+    float q[QN];
+    int32_t sub[SN > 0 ? SN : 1];
+};
+
+template <typename BLOB>
+struct BlobTraits {
+    static constexpr bool kHas = true;
+};
+template <>
+struct BlobTraits<NoBlob> {
+    static constexpr bool kHas = false;
+};
+
+template <typename T, int QB, bool VEC, typename BLOB>
+__global__ void __launch_bounds__(kScanThreads)
+scan_rows_kernel(const ScanArgs a, const __grid_constant__ BLOB blob) {
+    constexpr bool kBlob = BlobTraits<BLOB>::kHas;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NV = kRowsPerWarp * QB;
     const int dim = a.dim;
@@ -121,9 +150,13 @@ __global__ void __launch_bounds__(kScanThreads) scan_rows_kernel(const ScanArgs 
     const uint64_t floor_key = 0;  // the floor itself is tested in float (NaN-safe)
 
     // stage the queries (zero-fill unused slots)
-    for (int i = tid; i < QB * dim; i += kScanThreads) {
-        const int q = i / dim;
-        sq[i] = q < a.nq ? a.queries[i] : 0.0f;
+    if constexpr (kBlob) {
+        for (int i = tid; i < dim; i += kScanThreads) sq[i] = blob.q[i];
+    } else {
+        for (int i = tid; i < QB * dim; i += kScanThreads) {
+            const int q = i / dim;
+            sq[i] = q < a.nq ? a.queries[i] : 0.0f;
+        }
     }
     if (tid < QB) {
         s_cnt[tid] = 0;
@@ -149,17 +182,22 @@ __global__ void __launch_bounds__(kScanThreads) scan_rows_kernel(const ScanArgs 
 
         const int64_t pos0 = tile * kRoundRows + warp * kRowsPerWarp;
         const T* rp[kRowsPerWarp];
+        int64_t rrow[kRowsPerWarp];
 #pragma unroll
         for (int r = 0; r < kRowsPerWarp; ++r) {
             const int64_t pos = pos0 + r;
             int64_t row = 0;
             if (pos < a.n_scan) {
                 row = pos;
-                if (a.subset) {
+                if (kBlob && a.subset_in_params) {
+                    row = blob.sub[pos];
+                    if (row < 0) row += a.n_corpus;
+                } else if (a.subset) {
                     row = a.subset[pos];
                     if (row < 0) row += a.n_corpus;  // numpy-style negative ordinals
                 }
             }
+            rrow[r] = row;
             rp[r] = corpus + row * dim;
         }
 
@@ -214,10 +252,20 @@ __global__ void __launch_bounds__(kScanThreads) scan_rows_kernel(const ScanArgs 
             const int idx = lane / kLanesPerValue;
             const int r = idx / QB, q = idx % QB;
             const int64_t pos = pos0 + r;
-            if (pos < a.n_scan && q < a.nq) {
+            bool allowed = true;
+            if (a.row_mask) {  // predicate pushdown (vectorbase.py:191-201): one bit per corpus row
+                int64_t row = rrow[0];
+#pragma unroll
+                for (int rr = 1; rr < kRowsPerWarp; ++rr) row = (r == rr) ? rrow[rr] : row;
+                allowed = (a.row_mask[row >> 5] >> (row & 31)) & 1u;
+            }
+            if (pos < a.n_scan && q < a.nq && allowed) {
                 const float s = score_from_dot(acc[0]);
                 if (s >= a.floor_score) {  // float32 compare, as vectorbase.py:179
-                    const uint64_t key = make_key(s, static_cast<uint32_t>(pos));
+                    // ties_low: among equal scores the LOWER position sorts first (the reference's
+                    // stable sort on the predicate path), else the higher one (its argsort path)
+                    const uint32_t p32 = static_cast<uint32_t>(pos);
+                    const uint64_t key = make_key(s, a.ties_low ? ~p32 : p32);
                     if (key >= s_admit[q] && (a.bound == nullptr || key < a.bound[q])) {
                         CandList l{skeys + static_cast<size_t>(q) * cap, &s_cnt[q], &s_admit[q]};
                         need |= list_push(l, key, cap - kRoundRows);
@@ -242,6 +290,60 @@ __global__ void __launch_bounds__(kScanThreads) scan_rows_kernel(const ScanArgs 
             for (int i = tid; i < n; i += kScanThreads) dst[i] = l.keys[i];
         }
     }
+
+    if (a.fused) {
+        // ---- last CTA done: merge every CTA's survivors, write the hits, raise the host flag ----
+        __shared__ int s_is_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t t = atomicAdd(a.fused_ticket, 1u);
+            s_is_last = t == gridDim.x - 1;
+            if (s_is_last) *a.fused_ticket = 0;  // ready for the next search
+        }
+        __syncthreads();
+        if (!s_is_last) return;
+        __threadfence();
+        uint64_t* keys = skeys;  // the lists are dead now; room for kFusedSelectMax keys was reserved
+        for (int q = 0; q < a.nq; ++q) {
+            const int total = static_cast<int>(min(__ldcg(&a.cand_count[q]), static_cast<uint32_t>(a.cand_stride)));
+            int cap2 = 32;
+            while (cap2 < total) cap2 <<= 1;
+            const uint64_t* in = a.cand_keys + static_cast<size_t>(q) * a.cand_stride;
+            __syncthreads();
+            for (int i = tid; i < cap2; i += kScanThreads) keys[i] = i < total ? __ldcg(&in[i]) : 0;
+            bitonic_sort_desc<kScanThreads>(keys, cap2);
+            const int n = min(total, a.k);
+            int64_t* items = a.out_items + static_cast<size_t>(q) * a.k;
+            float* scores = a.out_scores + static_cast<size_t>(q) * a.k;
+            for (int j = tid; j < a.k; j += kScanThreads) {
+                int64_t item = -1;
+                float sc = 0.0f;
+                if (j < n) {
+                    const uint32_t kp = key_pos(keys[j]);
+                    const uint32_t pos = a.ties_low ? ~kp : kp;
+                    if (kBlob && a.subset_in_params) item = blob.sub[pos];
+                    else item = a.subset ? a.subset[pos] : static_cast<int64_t>(pos);
+                    item += a.item_offset;
+                    sc = key_score(keys[j]);
+                }
+                items[j] = item;
+                scores[j] = sc;
+            }
+            if (tid == 0) {
+                a.out_counts[q] = n;
+                a.cand_count[q] = 0;
+            }
+        }
+        if (a.done_flag) {
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) {
+                *reinterpret_cast<volatile uint32_t*>(a.done_flag) = a.done_seq;
+                __threadfence_system();
+            }
+        }
+    }
 }
 
 int scan_grid(int device, int dtype, int dim, int nq, int k, int64_t n_scan) {
@@ -259,25 +361,26 @@ int scan_grid(int device, int dtype, int dim, int nq, int k, int64_t n_scan) {
     return static_cast<int>(g);
 }
 
-template <typename T, int QB>
-static cudaError_t launch_scan_t(const ScanArgs& a, cudaStream_t s) {
+template <typename T, int QB, typename BLOB>
+static cudaError_t launch_scan_t(const ScanArgs& a, const BLOB& blob, cudaStream_t s) {
     const size_t row_bytes = static_cast<size_t>(a.dim) * sizeof(T);
     const bool vec = (row_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(a.corpus) % 16 == 0);
-    const size_t smem = scan_smem_bytes(QB, a.dim, a.k);
-    auto kern = vec ? scan_rows_kernel<T, QB, true> : scan_rows_kernel<T, QB, false>;
+    const size_t smem = scan_smem_bytes(QB, a.dim, a.k, a.fused != 0);
+    auto kern = vec ? scan_rows_kernel<T, QB, true, BLOB> : scan_rows_kernel<T, QB, false, BLOB>;
     static int granted[2][16] = {};
     cudaError_t e = ensure_dynamic_smem(kern, smem, granted[vec ? 1 : 0]);
     if (e != cudaSuccess) return e;
-    kern<<<a.grid, kScanThreads, smem, s>>>(a);
+    kern<<<a.grid, kScanThreads, smem, s>>>(a, blob);
     return cudaGetLastError();
 }
 
 template <typename T>
 static cudaError_t launch_scan_q(const ScanArgs& a, cudaStream_t s) {
-    if (a.nq <= 1) return launch_scan_t<T, 1>(a, s);
-    if (a.nq <= 2) return launch_scan_t<T, 2>(a, s);
-    if (a.nq <= 4) return launch_scan_t<T, 4>(a, s);
-    return launch_scan_t<T, 8>(a, s);
+    const NoBlob none{};
+    if (a.nq <= 1) return launch_scan_t<T, 1>(a, none, s);
+    if (a.nq <= 2) return launch_scan_t<T, 2>(a, none, s);
+    if (a.nq <= 4) return launch_scan_t<T, 4>(a, none, s);
+    return launch_scan_t<T, 8>(a, none, s);
 }
 
 cudaError_t launch_scan(const ScanArgs& a, cudaStream_t s) {
@@ -285,6 +388,54 @@ cudaError_t launch_scan(const ScanArgs& a, cudaStream_t s) {
         case TAV_F32: return launch_scan_q<float>(a, s);
         case TAV_BF16: return launch_scan_q<__nv_bfloat16>(a, s);
         case TAV_F16: return launch_scan_q<__half>(a, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ---- single-lookup latency form: query (and a short subset) in the kernel parameters ----------
+using SmallBlob = ParamBlob<kParamQuerySmall, 0>;
+using BigBlob = ParamBlob<kParamQueryBig, kParamSubsetMax>;
+
+bool scan1_fits(int dim, int k, int64_t n_scan, int64_t subset_len, bool has_subset) {
+    if (dim > kParamQueryBig) return false;
+    if (has_subset && subset_len > kParamSubsetMax) return false;
+    // the last CTA sorts every CTA's k survivors at once: a full wave of CTAs must fit its buffer
+    const int64_t tiles = (n_scan + kRoundRows - 1) / kRoundRows;
+    return static_cast<int64_t>(k) * std::min<int64_t>(tiles, 148) <= kFusedSelectMax;
+}
+
+int scan1_grid(int device, int dim, int k, int64_t n_scan) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int64_t tiles = (n_scan + kRoundRows - 1) / kRoundRows;
+    int64_t g = std::min<int64_t>(tiles, sms);          // one wave: the last CTA's merge stays short
+    g = std::min<int64_t>(g, kFusedSelectMax / std::max(k, 1));
+    (void)dim;
+    return static_cast<int>(std::max<int64_t>(g, 1));
+}
+
+template <typename T, typename BLOB>
+static cudaError_t launch_scan1_t(const ScanArgs& a, const float* q_host, const int64_t* sub_host, cudaStream_t s) {
+    // the blob is filled on the host stack and copied into the launch's parameter buffer
+    static thread_local BLOB blob;
+    memcpy(blob.q, q_host, static_cast<size_t>(a.dim) * sizeof(float));
+    if (sub_host)
+        for (int64_t i = 0; i < a.n_scan; ++i) blob.sub[i] = static_cast<int32_t>(sub_host[i]);
+    return launch_scan_t<T, 1>(a, blob, s);
+}
+
+cudaError_t launch_scan1(const ScanArgs& a, const float* q_host, const int64_t* sub_host, cudaStream_t s) {
+    const bool small = a.dim <= kParamQuerySmall && !sub_host;
+    switch (a.dtype) {
+        case TAV_F32:
+            return small ? launch_scan1_t<float, SmallBlob>(a, q_host, sub_host, s)
+                         : launch_scan1_t<float, BigBlob>(a, q_host, sub_host, s);
+        case TAV_BF16:
+            return small ? launch_scan1_t<__nv_bfloat16, SmallBlob>(a, q_host, sub_host, s)
+                         : launch_scan1_t<__nv_bfloat16, BigBlob>(a, q_host, sub_host, s);
+        case TAV_F16:
+            return small ? launch_scan1_t<__half, SmallBlob>(a, q_host, sub_host, s)
+                         : launch_scan1_t<__half, BigBlob>(a, q_host, sub_host, s);
     }
     return cudaErrorInvalidValue;
 }
@@ -324,7 +475,7 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(const SelectArgs
     for (int j = tid; j < a.k; j += kSelectThreads) {
         if (j < n) {
             const uint64_t key = keys[j];
-            const uint32_t pos = key_pos(key);
+            const uint32_t pos = a.ties_low ? ~key_pos(key) : key_pos(key);
             const int64_t item = a.subset ? a.subset[pos] : static_cast<int64_t>(pos);
             items[j] = item + a.item_offset;
             scores[j] = key_score(key);
@@ -420,6 +571,77 @@ cudaError_t launch_merge(int n_lists, int n_queries, int k, const int64_t* items
                                                          counts, items_stride, scores_stride,
                                                          counts_stride, out_items, out_scores,
                                                          out_counts);
+    return cudaGetLastError();
+}
+
+// ---- chunk -> message fold of a hit list (storage/memory/messageindex.py:185-207) --------------
+// The reference folds AFTER the top-k over chunks: walking the hits in score order, the first hit of
+// a message carries its best score; later hits of the same message are dropped.  One CTA per query,
+// in place: items become group (message) ordinals, order preserved, tail padded with -1 / 0.
+__global__ void __launch_bounds__(256)
+fold_groups_kernel(int k, const int32_t* row_to_group, int64_t n_rows, int64_t item_offset, int64_t* items_all,
+                   float* scores_all, int32_t* counts) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t* grp = reinterpret_cast<int32_t*>(smem_raw);         // [k]
+    float* sc = reinterpret_cast<float*>(grp + k);               // [k]
+    __shared__ int s_base, s_warp[8];
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t* items = items_all + static_cast<size_t>(q) * k;
+    float* scores = scores_all + static_cast<size_t>(q) * k;
+    const int n = min(counts[q], k);
+    for (int j = tid; j < n; j += 256) {
+        const int64_t row = items[j] - item_offset;
+        grp[j] = (row >= 0 && row < n_rows) ? row_to_group[row] : -1 - j;  // unmapped rows stay distinct
+        sc[j] = scores[j];
+    }
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < n; j0 += 256) {
+        const int j = j0 + tid;
+        bool keep = j < n;
+        if (keep) {
+            const int g = grp[j];
+            for (int i = 0; i < j; ++i)
+                if (grp[i] == g) {
+                    keep = false;
+                    break;
+                }
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (keep) {
+            const int dst = before + __popc(m & ((1u << lane) - 1u));
+            items[dst] = grp[j] < 0 ? -1 : static_cast<int64_t>(grp[j]);  // dst <= j; inputs were copied to smem
+            scores[dst] = sc[j];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int total = 0;
+            for (int w = 0; w < 8; ++w) total += s_warp[w];
+            s_base += total;
+        }
+        __syncthreads();
+    }
+    const int kept = s_base;
+    for (int j = kept + tid; j < k; j += 256) {
+        items[j] = -1;
+        scores[j] = 0.0f;
+    }
+    if (tid == 0) counts[q] = kept;
+}
+
+cudaError_t launch_fold_groups(int n_queries, int k, const int32_t* row_to_group, int64_t n_rows,
+                               int64_t item_offset, int64_t* items, float* scores, int32_t* counts,
+                               cudaStream_t s) {
+    if (n_queries == 0) return cudaSuccess;
+    const size_t smem = static_cast<size_t>(k) * 8;
+    static int granted[16] = {};
+    cudaError_t e = ensure_dynamic_smem(fold_groups_kernel, smem, granted);
+    if (e != cudaSuccess) return e;
+    fold_groups_kernel<<<n_queries, 256, smem, s>>>(k, row_to_group, n_rows, item_offset, items, scores, counts);
     return cudaGetLastError();
 }
 

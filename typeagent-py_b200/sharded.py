@@ -231,12 +231,20 @@ class ShardedVectorBase:
             return 0
         local, b, k, out = pending
         self._pending = None
-        redone = self._engine.finish()
-        total = redone
+        # a local failure must not leave the other ranks waiting in the collective: reduce an error
+        # flag together with the count and raise on every rank
+        error = None
+        try:
+            redone = self._engine.finish()
+        except Exception as e:  # noqa: BLE001
+            error, redone = e, 0
+        total, failed = redone, int(error is not None)
         if self.world > 1:
-            t = torch.tensor([redone], dtype=torch.int32, device=local.device)
+            t = torch.tensor([redone, failed], dtype=torch.int32, device=local.device)
             self._dist.all_reduce(t, group=self._group)
-            total = int(t.item())
+            total, failed = int(t[0].item()), int(t[1].item())
+        if failed:
+            raise error if error is not None else RuntimeError("finish(): another rank failed its exact fallback")
         if total > 0:  # some shard corrected its candidates: exchange and merge again, in place
             items, scores, counts = self._gather_and_merge(local, b, k)
             out[0].copy_(items), out[1].copy_(scores), out[2].copy_(counts)

@@ -13,7 +13,9 @@ Additions (not in the reference; all opt-in):
   * ``fuzzy_lookup_embeddings`` / ``search_arrays`` — batched lookups, the replacement for
     the one-query-at-a-time loops in storage/memory/reltermsindex.py:320-332 and
     storage/sqlite/reltermsindex.py:259-271;
-  * constructor keywords ``device``, ``storage_dtype``, ``normalize``, ``host_mirror``;
+  * ``search_arrays(..., allowed=mask)`` — predicate / post-filter pushdown as a row bitmask
+    evaluated inside the kernels (vectorbase.py:191-201, storage/sqlite/messageindex.py:296-326);
+  * constructor keywords ``device``, ``storage_dtype``, ``normalize``;
   * ``from_device_tensor`` / ``search_device`` — torch tensors as device-memory handles.
 
 Documented divergences: negative ``max_hits`` raises ``ValueError`` (the reference returns
@@ -123,8 +125,11 @@ class VectorBase:
         self._device_only_rows = 0  # rows living only on the device (from_device_tensor)
         self._adopted_tensor = None
         self._single_out: dict[int, tuple] = {}  # k -> reusable result arrays of fuzzy_lookup_embedding
-        self.force_path: str | None = None  # "scan" | "mma" | None (tests / benchmarks)
+        self.force_path: str | None = None  # "scan" | "mma" | "scan2" (two-kernel scan) | None (tests / benchmarks)
         self._timing = False
+        self._pending: list = []             # tensors of deferred device searches, kept alive until finish_search()
+        self._mask_key = None                # identity of the row mask currently on the device
+        self._predicate_masks: dict = {}     # (id(predicate), generation, n) -> packed bitmask
         self.clear()
 
     # ------------------------------------------------------------------ housekeeping
@@ -301,7 +306,9 @@ class VectorBase:
                 return self._ensure_device()
             self._ix_rows = 0
             self._ix_generation = self._generation
+            self._mask_key = None
         if self._ix_rows < self._count:
+            self._mask_key = None
             fresh = np.ascontiguousarray(self._buf[self._ix_rows : self._count])
             _capi.check(
                 lib.tav_append(self._ix, fresh.ctypes.data_as(C.c_void_p), len(fresh),
@@ -313,9 +320,36 @@ class VectorBase:
     def _flags(self) -> int:
         if self.force_path == "scan":
             return _capi.TAV_FORCE_SCAN
+        if self.force_path == "scan2":
+            return _capi.TAV_FORCE_SCAN | _capi.TAV_NO_FUSED_SCAN
         if self.force_path == "mma":
             return _capi.TAV_FORCE_MMA
         return 0
+
+    # ------------------------------------------------------------------ row masks
+    @staticmethod
+    def pack_row_mask(allowed) -> np.ndarray:
+        """bool [N] -> little-endian bit-packed uint32 words (bit r of word r // 32 = row r)."""
+        bits = np.packbits(np.asarray(allowed, dtype=bool), bitorder="little")
+        pad = (-len(bits)) % 4
+        if pad:
+            bits = np.concatenate([bits, np.zeros(pad, np.uint8)])
+        return np.ascontiguousarray(bits).view(np.uint32)
+
+    def _use_row_mask(self, lib, ix, allowed, key=None) -> None:
+        """Upload ``allowed`` (bool [N], or packed uint32 words) unless it is the mask already
+        on the device.  Masks are treated as immutable: identity + row generation is the key."""
+        n = len(self)
+        if key is None:
+            key = (id(allowed), self._generation, n)
+        if self._mask_key == key:
+            return
+        words = allowed if getattr(allowed, "dtype", None) == np.uint32 else self.pack_row_mask(allowed)
+        if len(words) != (n + 31) // 32:
+            raise ValueError(f"row mask has {len(words) * 32} bits for {n} rows")
+        words = np.ascontiguousarray(words)
+        _capi.check(lib.tav_set_row_mask(ix, words.ctypes.data_as(C.c_void_p), n, 0, None))
+        self._mask_key = key
 
     def _check_queries(self, queries) -> np.ndarray:
         q = np.ascontiguousarray(queries, dtype=np.float32)
@@ -334,11 +368,16 @@ class VectorBase:
         min_score: float = 0.0,
         subset: Sequence[int] | np.ndarray | None = None,
         out: tuple[np.ndarray, np.ndarray, np.ndarray] | None = None,
+        allowed: np.ndarray | None = None,
+        ties_low_first: bool = False,
+        _mask_key=None,
     ) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
         """Batched lookup returning arrays: items int64 [B, k], scores float32 [B, k],
         counts int32 [B] (entries beyond counts[b] are padding: item -1, score 0).  `k` is
         clamped to the number of rows searched.  ``out`` may supply preallocated (e.g. pinned)
-        C-contiguous result arrays of exactly those shapes and dtypes."""
+        C-contiguous result arrays of exactly those shapes and dtypes.  ``allowed`` (bool [N] or
+        bit-packed uint32) restricts the lookup to rows whose bit is set, inside the kernels;
+        ``ties_low_first`` orders exactly equal scores by ascending ordinal (row-scan path)."""
         q = self._check_queries(queries)
         b = len(q)
         if k < 1:
@@ -368,9 +407,17 @@ class VectorBase:
         if b == 0 or n_rows == 0 or len(self) == 0 or np.isnan(floor):
             return items, scores, counts
         lib, ix = self._ensure_device()
+        flags = self._flags()
+        if allowed is not None:
+            if sub is not None:
+                raise ValueError("allowed= and subset= cannot be combined")
+            self._use_row_mask(lib, ix, allowed, _mask_key)
+            flags |= _capi.TAV_USE_ROW_MASK
+        if ties_low_first:
+            flags |= _capi.TAV_TIES_LOW_FIRST
         _capi.check(
             lib.tav_search(
-                ix, q.ctypes.data_as(C.c_void_p), b, k_eff, C.c_float(float(floor)), self._flags(),
+                ix, q.ctypes.data_as(C.c_void_p), b, k_eff, C.c_float(float(floor)), flags,
                 sub.ctypes.data_as(C.c_void_p) if sub is not None else None,
                 len(sub) if sub is not None else 0, 0,
                 items.ctypes.data_as(C.c_void_p), scores.ctypes.data_as(C.c_void_p),
@@ -427,6 +474,8 @@ class VectorBase:
             return []
         k = self._resolve_k(max_hits, n)
         if predicate is not None:
+            if max_hits == 0:  # the reference's predicate path slices `[:0]` (vectorbase.py:201)
+                return []
             return self._lookup_with_predicate(embedding, k, min_score, predicate)
         # single-lookup latency path: result buffers are reused across calls (they never escape:
         # the hits are copied into ScoredInt objects right here)
@@ -441,13 +490,33 @@ class VectorBase:
         c = int(counts[0])
         return [ScoredInt(i, s) for i, s in zip(items[0, :c].tolist(), scores[0, :c].tolist())]
 
+    _PREDICATE_MASK_ROWS = 65536  # below this many rows the predicate is evaluated up front
+
+    def _predicate_mask(self, predicate) -> tuple[np.ndarray, tuple]:
+        """The predicate over every row, bit-packed and cached per (predicate, rows)."""
+        n = len(self)
+        key = (id(predicate), self._generation, n)
+        hit = self._predicate_masks.get(key)
+        if hit is None:
+            if len(self._predicate_masks) > 8:
+                self._predicate_masks.clear()
+            accepted = np.fromiter((bool(predicate(i)) for i in range(n)), dtype=bool, count=n)
+            hit = self._predicate_masks[key] = (self.pack_row_mask(accepted), predicate)  # keeps id() alive
+        return hit[0], key
+
     def _lookup_with_predicate(self, embedding, k, min_score, predicate) -> list[ScoredInt]:
         """Reference semantics (vectorbase.py:191-201): every row at or above min_score that
-        satisfies the predicate, stable-sorted by descending score, first k.  The GPU returns
-        score-ordered pages; pages are fetched until k accepted rows are known to be final."""
+        satisfies the predicate, stable-sorted by descending score, first k.
+
+        The predicate is pushed down as a row bitmask tested inside the scan kernel (one search,
+        exact reference order including ties: equal scores -> lower ordinal first).  Small indexes
+        evaluate the predicate over all rows at once (cached); large ones first try one unfiltered
+        page of hits — enough whenever min_score or the predicate is not very selective — and only
+        then build the mask (O(N) predicate calls, what the reference itself spends at
+        min_score = 0)."""
         n = len(self)
-        fetch = min(n, max(4 * k, 64))
-        while True:
+        if n > self._PREDICATE_MASK_ROWS and (id(predicate), self._generation, n) not in self._predicate_masks:
+            fetch = min(n, max(4 * k, 64))
             items, scores, counts = self.search_arrays(embedding, fetch, min_score)
             c = int(counts[0])
             rows, vals = items[0, :c], scores[0, :c]
@@ -456,11 +525,15 @@ class VectorBase:
                 ScoredInt(int(rows[j]), float(vals[j])) for j in order if predicate(int(rows[j]))
             ]
             exhausted = c < fetch or fetch >= n
-            # rows tied with the last fetched score may continue on the next page
+            # rows tied with the last fetched score may continue beyond the page
             settled = len(accepted) >= k and (c == 0 or accepted[k - 1].score > float(vals[c - 1]))
             if exhausted or settled:
                 return accepted[:k]
-            fetch = min(n, fetch * 4)
+        mask, key = self._predicate_mask(predicate)
+        items, scores, counts = self.search_arrays(embedding, k, min_score, allowed=mask,
+                                                   ties_low_first=True, _mask_key=key)
+        c = int(counts[0])
+        return [ScoredInt(i, s_) for i, s_ in zip(items[0, :c].tolist(), scores[0, :c].tolist())]
 
     def fuzzy_lookup_embedding_in_subset(
         self,
@@ -551,12 +624,15 @@ class VectorBase:
         return self
 
     def search_device(self, queries, k: int, min_score: float = 0.0, item_offset: int = 0, out=None,
-                      defer_check: bool = False):
+                      defer_check: bool = False, allowed=None, row_to_group=None):
         """Lookup with torch CUDA tensors as handles, enqueued on torch's current stream:
         queries float32 [B, D] -> (items int64 [B,k], scores float32 [B,k], counts int32 [B]) on
         the device.  The tensor-core path normally ends with one host synchronisation (did any
         query need the exact fallback?); with ``defer_check=True`` the call is fully
-        asynchronous and ``finish_search()`` must run before the results are trusted."""
+        asynchronous and ``finish_search()`` must run before the results are trusted.
+        ``allowed``: row bitmask (see ``search_arrays``).  ``row_to_group``: int32 CUDA tensor [N];
+        the hits are then folded on the device like the reference's chunk -> message fold
+        (storage/memory/messageindex.py:185-207): first hit per group, items = group ordinals."""
         import torch
 
         if not (queries.is_cuda and queries.dtype == torch.float32 and queries.is_contiguous()):
@@ -575,8 +651,11 @@ class VectorBase:
         items, scores, counts = out
         stream = torch.cuda.current_stream(queries.device).cuda_stream
         flags = _capi.TAV_QUERIES_ON_DEVICE | _capi.TAV_OUTPUTS_ON_DEVICE | self._flags()
-        if defer_check:
+        if defer_check and row_to_group is None:
             flags |= _capi.TAV_DEFER_RETRY
+        if allowed is not None:
+            self._use_row_mask(lib, ix, allowed)
+            flags |= _capi.TAV_USE_ROW_MASK
         floor = float(np.float32(min_score))
         _capi.check(
             lib.tav_search(ix, C.c_void_p(queries.data_ptr()), b, k, C.c_float(floor),
@@ -584,23 +663,28 @@ class VectorBase:
                            C.c_void_p(scores.data_ptr()), C.c_void_p(counts.data_ptr()),
                            C.c_void_p(stream))
         )
-        # arguments (and tensors, kept alive) a deferred call must repeat in finish_search()
-        self._pending = (queries, b, k, floor, item_offset, items, scores, counts, stream) if defer_check else None
+        if row_to_group is not None:
+            if not (row_to_group.is_cuda and row_to_group.dtype == torch.int32 and row_to_group.is_contiguous()):
+                raise ValueError("row_to_group must be a contiguous int32 CUDA tensor")
+            _capi.check(
+                lib.tav_fold_groups(self._device, b, k, C.c_void_p(row_to_group.data_ptr()), row_to_group.numel(),
+                                    item_offset, C.c_void_p(items.data_ptr()), C.c_void_p(scores.data_ptr()),
+                                    C.c_void_p(counts.data_ptr()), C.c_void_p(stream))
+            )
+        if flags & _capi.TAV_DEFER_RETRY:
+            # the library redoes flagged queries into these very buffers at finish_search(): keep them alive
+            self._pending.append((queries, items, scores, counts, stream))
         return items, scores, counts
 
     def finish_search(self) -> int:
-        """Complete a ``search_device(..., defer_check=True)``: synchronise, redo (exactly) the
-        queries the tensor-core path flagged, return how many there were."""
-        pending = getattr(self, "_pending", None)
-        if pending is None:
+        """Complete every outstanding ``search_device(..., defer_check=True)``: synchronise, redo
+        (exactly) the queries the tensor-core path flagged, return how many there were."""
+        if not self._pending:
             return 0
-        queries, b, k, floor, item_offset, items, scores, counts, stream = pending
-        self._pending = None
+        stream = self._pending[-1][4]
         redone = C.c_int(0)
-        _capi.check(
-            _capi.load().tav_finish_search(self._ix, C.c_void_p(queries.data_ptr()), b, k, C.c_float(floor),
-                                           item_offset, C.c_void_p(items.data_ptr()),
-                                           C.c_void_p(scores.data_ptr()), C.c_void_p(counts.data_ptr()),
-                                           C.c_void_p(stream), C.byref(redone))
-        )
+        try:
+            _capi.check(_capi.load().tav_finish_search(self._ix, C.c_void_p(stream), C.byref(redone)))
+        finally:
+            self._pending.clear()
         return redone.value
