@@ -515,8 +515,8 @@ def measure(bn: Bench, name, w, steps, warmup, *, force=None, sustain_s=0.0, par
             e0.record()
             for i in range(n_steps):
                 step_resident()
-                if (i & 31) == 31:
-                    finish_resident()      # at most 64 searches may be outstanding
+                if (i & 7) == 7:
+                    finish_resident()      # at most 8 (sharded) / 64 searches may be outstanding
             finish_resident()
             e1.record()
             bn.barrier()

@@ -162,6 +162,36 @@ int tav_merge_topk(int device, int n_lists, int n_queries, int k, const int64_t*
                    float* out_scores, int32_t* out_counts, void* stream);
 
 /*
+ * Row-sharded search across the GPUs of one box, one process per GPU.  A group is
+ * this rank's end of the candidate exchange: an "exchange region" in its HBM which the peers map
+ * through a CUDA IPC handle.  Create it on every rank with the same arguments, exchange the handles
+ * (tav_group_handle_bytes() bytes each, rank order) by any host-side means, connect, then search:
+ *
+ *   tav_sharded_search = tav_search on this rank's rows (ordinals shifted by item_offset)
+ *                        -> PUBLISH kernel: this rank's [B, k] list stored into every peer's region
+ *                           over NVLink, sequence flag released at system scope
+ *                        -> MERGE: waits for all ranks' flags, merges the world's lists (same total
+ *                           order as one GPU: bit-identical results), acknowledges to the peers.
+ *
+ * No NCCL call and no host synchronisation on this path.  SPMD: every rank calls it with the same
+ * n_queries and k, in the same order.  queries / outputs are device pointers; the merged result is
+ * replicated on every rank.  With TAV_DEFER_RETRY in `flags` up to `depth` searches may be
+ * outstanding before tav_sharded_finish (which also agrees, across ranks, whether any rank had to
+ * redo a query exactly and then repeats the exchange for the last search).
+ */
+typedef struct tav_group tav_group;
+int tav_group_handle_bytes(void);
+int tav_group_create(int device, int rank, int world, int max_queries, int max_k, int depth, tav_group** out);
+int tav_group_local_handle(tav_group* g, void* handle_out);
+int tav_group_connect(tav_group* g, const void* handles /* world x tav_group_handle_bytes() */);
+int tav_group_capacity(const tav_group* g, int* max_queries, int* max_k, int* depth);
+int tav_group_destroy(tav_group* g);
+int tav_sharded_search(tav_index* ix, tav_group* g, const float* queries_device, int n_queries, int k,
+                       float min_score, int flags, int64_t item_offset, int64_t* out_items, float* out_scores,
+                       int32_t* out_counts, void* stream);
+int tav_sharded_finish(tav_index* ix, tav_group* g, void* stream, int* redone_total);
+
+/*
  * Chunk -> message fold of hit lists, on the device, in place (storage/memory/messageindex.py:
  * 185-207 `to_scored_message_ordinals`; the reference folds AFTER the top-k over chunks): walking
  * each query's hits in score order, the first hit of a group keeps its score, later hits of the

@@ -5,10 +5,10 @@
         --master-port 29517 tools/multi_gpu_check.py
 
 Every rank builds the same seeded corpus on the host, keeps its own row block on its GPU
-(ShardedVectorBase over NCCL), and checks that the sharded lookup — local search, one packed
-all-gather of the candidates, merge kernel — is BIT-IDENTICAL to the single-GPU lookup over the
-whole corpus on that rank's GPU, for the float32 row-scan path and the bf16 tensor-core path,
-and agrees with the CPU oracle.
+(ShardedVectorBase), and checks that the sharded lookup — local search, candidate exchange (libtavec's
+peer-memory publish/merge over NVLink, and the NCCL all-gather form), merge kernel — is BIT-IDENTICAL to
+the single-GPU lookup over the whole corpus on that rank's GPU, for the float32 row-scan path, the
+float32 split form and the bf16 / fp16 tensor-core paths, and agrees with the CPU oracle.
 """
 import os
 import sys
@@ -32,12 +32,14 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     settings = tab.TextEmbeddingIndexSettings(O.FakeEmbeddingModel())
-    for storage, n, d, b, k, ms in (("float32", 30011, 96, 7, 25, 0.45), ("bfloat16", 200003, 256, 200, 100, 0.0),
-                                    ("float16", 70001, 128, 33, 10, 0.5), ("float32", 90001, 128, 40, 20, 0.0),
-                                    ("bfloat16", 120000, 64, 300, 5, 0.0)):
+    cases = (("float32", 30011, 96, 7, 25, 0.45), ("bfloat16", 200003, 256, 200, 100, 0.0),
+             ("float16", 70001, 128, 33, 10, 0.5), ("float32", 90001, 128, 40, 20, 0.0),
+             ("bfloat16", 120000, 64, 300, 5, 0.0), ("float16", 150000, 128, 1024 + 5, 100, 0.0))
+    for ci, (storage, n, d, b, k, ms) in enumerate(cases):
+        exchange = "nccl" if ci == 2 else "peer"
         v, q = O.make_corpus(n, d, seed=n, n_queries=b)
         vr, qr = O.round_to_storage(v, storage), O.round_to_storage(q, storage)
-        sh = ShardedVectorBase(settings, device=local, storage_dtype=storage)
+        sh = ShardedVectorBase(settings, device=local, storage_dtype=storage, exchange=exchange)
         sh.deserialize(v)
         whole = tab.VectorBase(settings, device=local, storage_dtype=storage)
         whole.add_embeddings(None, v)
@@ -52,25 +54,34 @@ def main():
         for i in range(min(b, 5)):
             assert_hits_match({"items": got[0][i, : got[2][i]].tolist(), "scores": got[1][i, : got[2][i]].tolist()},
                               O.lookup(vr, qr[i], k, ms), min_score=ms)
+        # pipelined: several deferred searches (different queries each), one finish
+        qd = [torch.from_numpy(np.ascontiguousarray(np.roll(qr, j, axis=0))).cuda() for j in range(3)]
+        outs = [sh.search_tensors(x, k, ms, defer_check=True) for x in qd]
+        assert sh.finish() == 0
+        torch.cuda.synchronize()
+        for j, (it, sc, ct) in enumerate(outs):
+            np.testing.assert_array_equal(np.roll(ct.cpu().numpy(), -j, axis=0), want[2])
+            np.testing.assert_array_equal(np.roll(it.cpu().numpy(), -j, axis=0)[:, :1], want[0][:, :1])
         # append goes to the last rank and is found globally
         sh.add_embeddings(None, qr[:3])
         hit = sh.fuzzy_lookup_embedding(qr[1], 1, 0.0)[0]
         assert hit.item == n + 1, hit
         dist.barrier()
         if rank == 0:
-            print(f"multi-gpu ok: world={world} {storage} n={n} d={d} b={b} k={k} path={whole.last_timing()['path']}",
-                  flush=True)
+            print(f"multi-gpu ok: world={world} {storage} n={n} d={d} b={b} k={k} path={whole.last_timing()['path']} "
+                  f"exchange={exchange}", flush=True)
     # pathological scores (all rows identical): every rank's tensor-core search flags its queries,
     # finish() redoes them exactly and repeats the exchange
     row = O.round_to_bfloat16(O.make_corpus(1, 64, seed=9)[0])
     same = np.repeat(row, 20000 * world, axis=0)
-    sh = ShardedVectorBase(settings, device=local, storage_dtype="bfloat16")
-    sh.deserialize(same)
-    items, scores, counts = sh.search_arrays(np.repeat(row, 3, axis=0), 6, 0.0)
-    n = len(same)
-    assert items.tolist() == [list(range(n - 1, n - 7, -1))] * 3, items
-    if rank == 0:
-        print(f"multi-gpu ok: world={world} exact fallback through finish()", flush=True)
+    for exchange in ("peer", "nccl"):
+        sh = ShardedVectorBase(settings, device=local, storage_dtype="bfloat16", exchange=exchange)
+        sh.deserialize(same)
+        items, scores, counts = sh.search_arrays(np.repeat(row, 3, axis=0), 6, 0.0)
+        n = len(same)
+        assert items.tolist() == [list(range(n - 1, n - 7, -1))] * 3, items
+        if rank == 0:
+            print(f"multi-gpu ok: world={world} exact fallback through finish() exchange={exchange}", flush=True)
     dist.destroy_process_group()
 
 

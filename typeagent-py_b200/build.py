@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtavec.so")
 STAMP = os.path.join(HERE, ".libtavec.stamp")
-SOURCES = ["tav_api.cu", "tav_scan.cu", "tav_mma.cu"]
+SOURCES = ["tav_api.cu", "tav_scan.cu", "tav_mma.cu", "tav_group.cu"]
 HEADERS = ["tav_common.cuh", "tav_internal.h", "tav_ptx.cuh", "../../include/tavec.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

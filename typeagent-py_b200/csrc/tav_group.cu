@@ -1,0 +1,416 @@
+// tav_group.cu — the row-sharded search of libtavec over the GPUs of one NVSwitch box
+// (include/tavec.h: tav_group_*, tav_sharded_search, tav_sharded_finish).
+//
+// The reference has one VectorBase over the whole corpus (aitools/vectorbase.py:163-201); sharded,
+// every rank searches its contiguous row block and the per-rank [B, k] candidate lists are merged
+// (top-k is a decomposable reduction).  The exchange is NOT a library collective: every rank owns an
+// "exchange region" in its HBM, exported to its peers as a CUDA IPC handle; after the local search a
+// PUBLISH kernel stores this rank's packed list straight into every peer's region over NVLink (plain
+// st.global on peer-mapped pointers) and raises a sequence flag with a system-scope release; the MERGE
+// kernel of every rank spins (acquire) until all ranks' flags reached the search's sequence number,
+// merges the world's lists from its own HBM and acknowledges to the peers, so that a slot is never
+// overwritten while a slower rank still reads it.  One process per GPU; the handles travel once,
+// through whatever the host side has (torch.distributed.all_gather_object in the Python class).
+//
+// Region layout (device memory of the owning rank):
+//   arrive[world]  u32   arrive[r] = sequence number of the last search rank r PUBLISHED here
+//   ack[world]     u32   ack[r]    = sequence number of the last search rank r MERGED (it no longer
+//                                    reads what this rank published for it)
+//   redo[2][world] u32   finish protocol: (finish_seq << 8 | min(redone, 255)) + 1 per rank
+//   slots[depth][world][slot_bytes]   packed lists [items i64 | scores f32 | counts i32] (8-byte aligned
+//                                    sections, the layout ShardedVectorBase always used)
+// `depth` searches may be in flight (deferred) before a rank has to wait for its peers' acks.
+
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "tav_common.cuh"
+#include "tav_internal.h"
+
+namespace tav {
+
+namespace {
+
+constexpr int kMaxWorld = 16;
+constexpr long long kSpinLimit = 8000000000ll;  // ~4 s of clock64: a lost peer traps instead of hanging the box
+
+struct PeerTable {
+    char* region[kMaxWorld];  // region[r] = base of rank r's exchange region as mapped in THIS process
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// true once *p has reached `want` (sequence numbers wrap: compare as a signed distance)
+__device__ __forceinline__ void spin_until(const uint32_t* p, uint32_t want) {
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(ld_acquire_sys(p) - want) < 0) {
+        if (clock64() - t0 > kSpinLimit) __trap();
+        __nanosleep(64);
+    }
+}
+
+// Publish: this rank's packed list (already in its own slot of its own region) -> the same slot in
+// every peer's region, then arrive[me] = seq everywhere.  Waits first until every peer acknowledged
+// the search that used this slot `depth` searches ago.
+__global__ void __launch_bounds__(256)
+publish_kernel(PeerTable peers, int me, int world, size_t off_ack, size_t off_slot, size_t bytes, uint32_t seq,
+               uint32_t need_ack, uint32_t* ticket) {
+    __shared__ int s_last;
+    const char* src = peers.region[me] + off_slot;
+    if (blockIdx.x == 0 && threadIdx.x < world && threadIdx.x != me) {
+        // ack[r] lives in MY region, written by rank r
+        spin_until(reinterpret_cast<const uint32_t*>(peers.region[me] + off_ack) + threadIdx.x, need_ack);
+    }
+    // every CTA needs the acks before it overwrites peer slots: CTA 0 spins, the others wait on it via
+    // the ticket's high bit (set by CTA 0 once the acks are in)
+    if (blockIdx.x == 0) {
+        __syncthreads();
+        if (threadIdx.x == 0) atomicOr(ticket, 0x80000000u);
+    } else if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while (!(atomicAdd(ticket, 0u) & 0x80000000u)) {
+            if (clock64() - t0 > kSpinLimit) __trap();
+            __nanosleep(32);
+        }
+    }
+    __syncthreads();
+    const size_t n16 = bytes / 16;  // slot sections are 8-byte aligned and padded to 16 by the host side
+    for (int w = 0; w < world; ++w) {
+        if (w == me) continue;
+        uint4* dst = reinterpret_cast<uint4*>(peers.region[w] + off_slot);
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16;
+             i += static_cast<size_t>(gridDim.x) * blockDim.x)
+            dst[i] = s4[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t t = atomicAdd(ticket, 1u) & 0x7FFFFFFFu;
+        s_last = t == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x < world)
+            st_release_sys(reinterpret_cast<uint32_t*>(peers.region[threadIdx.x]) + me, seq);  // arrive[me] at rank w
+        if (threadIdx.x == 0) *ticket = 0;
+    }
+}
+
+// first kernel of a merge: wait for every rank's publish of `seq` (one tiny CTA; the merge kernel that
+// follows in stream order then reads complete lists)
+__global__ void wait_arrive_kernel(const uint32_t* arrive, int world, uint32_t seq) {
+    if (threadIdx.x < world) spin_until(arrive + threadIdx.x, seq);
+}
+
+// last kernel of a merge: tell every peer that this rank is done reading the slots of `seq`
+__global__ void ack_kernel(PeerTable peers, int me, int world, size_t off_ack, uint32_t seq) {
+    if (threadIdx.x < world && threadIdx.x != me)
+        st_release_sys(reinterpret_cast<uint32_t*>(peers.region[threadIdx.x] + off_ack) + me, seq);
+}
+
+// finish protocol: publish this rank's count of exactly-redone queries, wait for everybody's, sum
+__global__ void redo_exchange_kernel(PeerTable peers, int me, int world, size_t off_redo, uint32_t fin_seq,
+                                     uint32_t redone, uint32_t* total_host) {
+    const uint32_t tag = ((fin_seq << 8) | min(redone, 255u)) + 1u;
+    const size_t off = off_redo + static_cast<size_t>(fin_seq & 1u) * world * sizeof(uint32_t);
+    __shared__ uint32_t s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    if (threadIdx.x < world) {
+        st_release_sys(reinterpret_cast<uint32_t*>(peers.region[threadIdx.x] + off) + me, tag);
+        const uint32_t* mine = reinterpret_cast<const uint32_t*>(peers.region[me] + off) + threadIdx.x;
+        const long long t0 = clock64();
+        uint32_t v;
+        while ((((v = ld_acquire_sys(mine)) - 1u) >> 8) != (fin_seq & 0x00FFFFFFu) || v == 0) {
+            if (clock64() - t0 > kSpinLimit) __trap();
+            __nanosleep(64);
+        }
+        atomicAdd(&s_sum, (v - 1u) & 0xFFu);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *total_host = s_sum;
+        __threadfence_system();
+    }
+}
+
+}  // namespace
+
+}  // namespace tav
+
+using namespace tav;
+
+struct tav_group {
+    int device = 0, rank = 0, world = 1, depth = 2;
+    int max_queries = 0, max_k = 0;
+    size_t slot_bytes = 0, off_ack = 0, off_redo = 0, off_slots = 0, region_bytes = 0;
+    char* region = nullptr;           // this rank's exchange region (cudaMalloc)
+    PeerTable peers{};                // region of every rank, as mapped here
+    bool connected = false;
+    uint32_t seq = 0, fin_seq = 0;    // searches published / finishes exchanged so far
+    uint32_t* ticket = nullptr;       // device counter of the publish kernel
+    uint32_t* total_host = nullptr;   // pinned: result of the redo exchange
+    int64_t* merged_items = nullptr;  // where the last search's merged result went (for a re-merge at finish)
+    float* merged_scores = nullptr;
+    int32_t* merged_counts = nullptr;
+    int last_nq = 0, last_k = 0;
+    uint32_t last_seq = 0;
+    int outstanding = 0;              // deferred sharded searches since the last finish
+};
+
+static inline size_t a16(size_t v) { return (v + 15) & ~size_t(15); }
+static inline size_t a8(size_t v) { return (v + 7) & ~size_t(7); }
+
+// the packed layout of one rank's list (as typeagent_py_b200/sharded.py:packed_layout), padded to 16 bytes
+static void packed_offsets(int nq, int k, size_t* off_scores, size_t* off_counts, size_t* total) {
+    *off_scores = a8(static_cast<size_t>(nq) * k * 8);
+    *off_counts = *off_scores + a8(static_cast<size_t>(nq) * k * 4);
+    *total = a16(*off_counts + a8(static_cast<size_t>(nq) * 4));
+}
+
+#define TAVG_CUDA(expr)                                                                            \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return _e == cudaErrorMemoryAllocation ? TAV_ERR_OOM : TAV_ERR_CUDA;                   \
+        }                                                                                          \
+    } while (0)
+
+extern "C" {
+
+int tav_group_handle_bytes(void) { return static_cast<int>(sizeof(cudaIpcMemHandle_t)); }
+
+int tav_group_create(int device, int rank, int world, int max_queries, int max_k, int depth, tav_group** out) {
+    if (!out || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || max_queries < 1 || max_k < 1 ||
+        depth < 1 || depth > 64) {
+        set_error("tav_group_create: invalid argument (world <= %d, depth 1..64)", kMaxWorld);
+        return TAV_ERR_INVALID;
+    }
+    TAVG_CUDA(cudaSetDevice(device));
+    tav_group* g = new (std::nothrow) tav_group();
+    if (!g) return TAV_ERR_OOM;
+    g->device = device;
+    g->rank = rank;
+    g->world = world;
+    g->depth = depth;
+    g->max_queries = max_queries;
+    g->max_k = max_k;
+    size_t os, oc;
+    packed_offsets(max_queries, max_k, &os, &oc, &g->slot_bytes);
+    g->off_ack = a16(static_cast<size_t>(world) * 4);
+    g->off_redo = g->off_ack + a16(static_cast<size_t>(world) * 4);
+    g->off_slots = (g->off_redo + a16(static_cast<size_t>(2) * world * 4) + 255) & ~size_t(255);
+    g->region_bytes = g->off_slots + static_cast<size_t>(depth) * world * g->slot_bytes;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&g->region), g->region_bytes);
+    if (e == cudaSuccess) e = cudaMemset(g->region, 0, g->off_slots);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&g->ticket), 64);
+    if (e == cudaSuccess) e = cudaMemset(g->ticket, 0, 64);
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&g->total_host), 64);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        set_error("tav_group_create: %s", cudaGetErrorString(e));
+        tav_group_destroy(g);
+        return e == cudaErrorMemoryAllocation ? TAV_ERR_OOM : TAV_ERR_CUDA;
+    }
+    g->peers.region[rank] = g->region;
+    g->connected = world == 1;
+    *out = g;
+    return TAV_OK;
+}
+
+int tav_group_local_handle(tav_group* g, void* handle_out) {
+    if (!g || !handle_out) return TAV_ERR_INVALID;
+    TAVG_CUDA(cudaSetDevice(g->device));
+    cudaIpcMemHandle_t h;
+    TAVG_CUDA(cudaIpcGetMemHandle(&h, g->region));
+    memcpy(handle_out, &h, sizeof(h));
+    return TAV_OK;
+}
+
+int tav_group_connect(tav_group* g, const void* handles) {
+    if (!g || !handles) return TAV_ERR_INVALID;
+    TAVG_CUDA(cudaSetDevice(g->device));
+    for (int r = 0; r < g->world; ++r) {
+        if (r == g->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + static_cast<size_t>(r) * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        TAVG_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        g->peers.region[r] = static_cast<char*>(p);
+    }
+    g->connected = true;
+    return TAV_OK;
+}
+
+int tav_group_destroy(tav_group* g) {
+    if (!g) return TAV_OK;
+    cudaSetDevice(g->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < g->world; ++r)
+        if (r != g->rank && g->peers.region[r]) cudaIpcCloseMemHandle(g->peers.region[r]);
+    if (g->region) cudaFree(g->region);
+    if (g->ticket) cudaFree(g->ticket);
+    if (g->total_host) cudaFreeHost(g->total_host);
+    delete g;
+    return TAV_OK;
+}
+
+int tav_group_capacity(const tav_group* g, int* max_queries, int* max_k, int* depth) {
+    if (!g) return TAV_ERR_INVALID;
+    if (max_queries) *max_queries = g->max_queries;
+    if (max_k) *max_k = g->max_k;
+    if (depth) *depth = g->depth;
+    return TAV_OK;
+}
+
+// exchange + merge of the list this rank holds in its own slot for sequence number `seq`
+static int publish_and_merge(tav_group* g, int nq, int k, uint32_t seq, int64_t* out_items, float* out_scores,
+                             int32_t* out_counts, cudaStream_t s) {
+    const int slot = static_cast<int>(seq % static_cast<uint32_t>(g->depth));
+    size_t off_scores, off_counts, bytes;
+    packed_offsets(nq, k, &off_scores, &off_counts, &bytes);
+    const size_t off_mine = g->off_slots + (static_cast<size_t>(slot) * g->world + g->rank) * g->slot_bytes;
+    if (g->world > 1) {
+        const int grid = static_cast<int>(std::min<size_t>(32, std::max<size_t>(1, bytes / (16 * 256 * 4))));
+        // the slot was last used by search seq - depth: every peer must have merged that one
+        const uint32_t need_ack = seq - static_cast<uint32_t>(g->depth);
+        const uint32_t need = seq > static_cast<uint32_t>(g->depth) ? need_ack : 0u;
+        publish_kernel<<<grid, 256, 0, s>>>(g->peers, g->rank, g->world, g->off_ack, off_mine, bytes, seq, need,
+                                            g->ticket);
+        TAVG_CUDA(cudaGetLastError());
+        wait_arrive_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const uint32_t*>(g->region), g->world, seq);
+        TAVG_CUDA(cudaGetLastError());
+    }
+    // lists of all ranks for this slot lie side by side in MY region: strides between ranks = slot_bytes
+    const char* base = g->region + g->off_slots + static_cast<size_t>(slot) * g->world * g->slot_bytes;
+    TAVG_CUDA(launch_merge(g->world, nq, k, reinterpret_cast<const int64_t*>(base),
+                           reinterpret_cast<const float*>(base + off_scores),
+                           reinterpret_cast<const int32_t*>(base + off_counts),
+                           static_cast<int64_t>(g->slot_bytes / 8), static_cast<int64_t>(g->slot_bytes / 4),
+                           static_cast<int64_t>(g->slot_bytes / 4), out_items, out_scores, out_counts, s));
+    if (g->world > 1) {
+        ack_kernel<<<1, 32, 0, s>>>(g->peers, g->rank, g->world, g->off_ack, seq);
+        TAVG_CUDA(cudaGetLastError());
+    }
+    return TAV_OK;
+}
+
+int tav_sharded_search(tav_index* ix, tav_group* g, const float* queries_device, int n_queries, int k,
+                       float min_score, int flags, int64_t item_offset, int64_t* out_items, float* out_scores,
+                       int32_t* out_counts, void* stream) {
+    if (!ix || !g || n_queries < 1 || k < 1 || !queries_device || !out_items || !out_scores || !out_counts) {
+        set_error("tav_sharded_search: invalid argument");
+        return TAV_ERR_INVALID;
+    }
+    if (!g->connected) {
+        set_error("tav_sharded_search: tav_group_connect has not run");
+        return TAV_ERR_STATE;
+    }
+    if (n_queries > g->max_queries || k > g->max_k) {
+        set_error("tav_sharded_search: %d queries x top-%d exceed the group's capacity (%d x %d)", n_queries, k,
+                  g->max_queries, g->max_k);
+        return TAV_ERR_INVALID;
+    }
+    TAVG_CUDA(cudaSetDevice(g->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool defer = (flags & TAV_DEFER_RETRY) != 0;
+    if (defer && g->outstanding >= g->depth) {
+        set_error("tav_sharded_search: %d deferred searches outstanding (the group's depth); call tav_sharded_finish",
+                  g->outstanding);
+        return TAV_ERR_STATE;
+    }
+    const uint32_t seq = ++g->seq;
+    const int slot = static_cast<int>(seq % static_cast<uint32_t>(g->depth));
+    size_t off_scores, off_counts, bytes;
+    packed_offsets(n_queries, k, &off_scores, &off_counts, &bytes);
+    char* mine = g->region + g->off_slots + (static_cast<size_t>(slot) * g->world + g->rank) * g->slot_bytes;
+    // local search straight into this rank's slot (global ordinals through item_offset)
+    const int sflags = (flags & (TAV_FORCE_SCAN | TAV_FORCE_MMA | TAV_USE_ROW_MASK)) | TAV_QUERIES_ON_DEVICE |
+                       TAV_OUTPUTS_ON_DEVICE | TAV_DEFER_RETRY;
+    if (tav_size(ix) == 0) {
+        TAVG_CUDA(cudaMemsetAsync(mine + off_counts, 0, static_cast<size_t>(n_queries) * 4, s));
+    } else {
+        int rc = tav_search(ix, queries_device, n_queries, k, min_score, sflags, nullptr, 0, item_offset,
+                            reinterpret_cast<int64_t*>(mine), reinterpret_cast<float*>(mine + off_scores),
+                            reinterpret_cast<int32_t*>(mine + off_counts), stream);
+        if (rc != TAV_OK) return rc;
+    }
+    int rc = publish_and_merge(g, n_queries, k, seq, out_items, out_scores, out_counts, s);
+    if (rc != TAV_OK) return rc;
+    g->merged_items = out_items;
+    g->merged_scores = out_scores;
+    g->merged_counts = out_counts;
+    g->last_nq = n_queries;
+    g->last_k = k;
+    g->last_seq = seq;
+    g->outstanding += 1;
+    if (!defer) {
+        int redone = 0;
+        return tav_sharded_finish(ix, g, stream, &redone);
+    }
+    return TAV_OK;
+}
+
+int tav_sharded_finish(tav_index* ix, tav_group* g, void* stream, int* redone_total) {
+    if (!ix || !g) return TAV_ERR_INVALID;
+    if (redone_total) *redone_total = 0;
+    if (g->outstanding == 0) return TAV_OK;
+    TAVG_CUDA(cudaSetDevice(g->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int redone = 0;
+    int rc = tav_finish_search(ix, stream, &redone);  // synchronises; corrects this rank's slot(s) in place
+    if (rc != TAV_OK) return rc;
+    uint32_t total = static_cast<uint32_t>(redone);
+    if (g->world > 1) {
+        const uint32_t fin = ++g->fin_seq;
+        *g->total_host = 0;
+        redo_exchange_kernel<<<1, 32, 0, s>>>(g->peers, g->rank, g->world, g->off_redo, fin,
+                                              static_cast<uint32_t>(redone), g->total_host);
+        TAVG_CUDA(cudaGetLastError());
+        TAVG_CUDA(cudaStreamSynchronize(s));
+        total = *g->total_host;
+    }
+    const int outstanding = g->outstanding;
+    g->outstanding = 0;
+    if (total > 0) {
+        // Some rank corrected candidates it had already published: exchange and merge again.  Only the
+        // LAST search can be repaired (its slot and output pointers are known); with several deferred
+        // searches outstanding an earlier one may be stale — report it.
+        const uint32_t seq = ++g->seq;
+        const int old_slot = static_cast<int>(g->last_seq % static_cast<uint32_t>(g->depth));
+        const int new_slot = static_cast<int>(seq % static_cast<uint32_t>(g->depth));
+        if (new_slot != old_slot) {
+            size_t os, oc, bytes;
+            packed_offsets(g->last_nq, g->last_k, &os, &oc, &bytes);
+            const char* from = g->region + g->off_slots + (static_cast<size_t>(old_slot) * g->world + g->rank) * g->slot_bytes;
+            char* to = g->region + g->off_slots + (static_cast<size_t>(new_slot) * g->world + g->rank) * g->slot_bytes;
+            TAVG_CUDA(cudaMemcpyAsync(to, from, bytes, cudaMemcpyDeviceToDevice, s));
+        }
+        rc = publish_and_merge(g, g->last_nq, g->last_k, seq, g->merged_items, g->merged_scores, g->merged_counts, s);
+        if (rc != TAV_OK) return rc;
+        TAVG_CUDA(cudaStreamSynchronize(s));
+        if (outstanding > 1) {
+            if (redone_total) *redone_total = static_cast<int>(total);
+            set_error("tav_sharded_finish: %u queries needed the exact fallback while %d sharded searches were "
+                      "outstanding; only the last one was re-merged", total, outstanding);
+            return TAV_ERR_STATE;
+        }
+    }
+    if (redone_total) *redone_total = static_cast<int>(total);
+    return TAV_OK;
+}
+
+}  // extern "C"

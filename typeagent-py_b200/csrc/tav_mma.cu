@@ -76,7 +76,8 @@ constexpr int kEpiCols = kBN / 2;                   // columns per epilogue warp
 constexpr int kSampleTop = 8;                       // the threshold is the 8th largest block maximum
 constexpr int kTmemCols = 512;
 constexpr int kMaxChunks = 512;                      // query chunks per launch (tav_search slabs larger batches)
-constexpr int kFinalizeFast = 4096;                 // finalize sorts up to this many candidates in one go
+constexpr int kFinalizeFast = 8192;                 // finalize sorts up to this many candidates in one go
+constexpr int kMaxSegments = 320;                   // candidate segments per query (2 per unit of its chunk)
 // both forms: 192 KB of tiles + barriers + a small scratch used by the sampler's tail
 constexpr size_t kScratchBytes = 2 * 128 * kSampleTop * sizeof(float);
 constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(4) * kStageBytes + 256 + kScratchBytes;
@@ -92,16 +93,16 @@ struct KernelArgs {
     int nq;                // valid queries (all chunks)
     int nqc;               // query chunks of 128 * CG queries
     int nq_pad;            // nqc * 128 * CG
-    int chunk_bound;       // 1: unit u serves only chunk u % nqc (SAMPLE); 0: items strided over units
+    int n_seg;             // MAIN: candidate segments per query = 2 * (units per chunk)
     float* thr;            // [nq_pad] admission threshold (raw dot) per query: SAMPLE writes, MAIN reads
     float* floor_x;        // SAMPLE: [nq_pad] the caller's min_score as a dot floor
     float* sample_max;     // SAMPLE: [n_tiles_work * 2, nq_pad] block maxima
     uint32_t* sample_done; // SAMPLE: [nqc * CG] finished-unit counters (self-resetting)
     int32_t* retry;        // SAMPLE: [nq] per-query "redo exactly" flags, cleared here
     float floor_score;     // SAMPLE: (float)min_score
-    uint64_t* cand;        // MAIN: [nq_pad, capg]  (dot bits << 32 | row)
-    uint32_t* cand_count;  // MAIN: [nq_pad]  (SAMPLE clears it)
-    uint32_t capg;
+    uint64_t* cand;        // MAIN: [nq_pad, n_seg, cap_seg]  (dot bits << 32 | row)
+    uint32_t* cand_count;  // MAIN: [nq_pad, n_seg] rows each epilogue thread admitted (may exceed cap_seg: overflow)
+    uint32_t cap_seg;
     const uint32_t* row_mask;  // optional: bit r set = row r may be returned
     float* dump;           // DUMP: [nq, n_rows] raw dots
 };
@@ -116,19 +117,16 @@ __device__ __forceinline__ void insert_top(float (&top)[kSampleTop], float x) {
     }
 }
 
-// item i of unit `unit` -> (visited tile t, query chunk c); false when the unit has no such item
+// Work distribution: unit u (a CTA, or a CTA pair) serves ONE query chunk, c = u % nqc, and every
+// (n_units / nqc)-th tile of the launch, starting at u / nqc — so the nqc units that share a tile run
+// side by side (the tile is fetched from HBM once and served to the others by L2) and an epilogue
+// thread keeps the same query for the whole launch (its candidate counter lives in a register).
+// Item i of unit `unit` -> (visited tile t, query chunk c); false when the unit has no such item.
 __device__ __forceinline__ bool get_item(const KernelArgs& a, int unit, int n_units, int i, int& t, int& c) {
-    if (a.chunk_bound) {
-        const int upc = n_units / a.nqc;  // units per chunk (the launcher makes n_units a multiple of nqc)
-        c = unit % a.nqc;
-        t = unit / a.nqc + i * upc;
-        return t < a.n_tiles_work;
-    }
-    const int64_t w = unit + static_cast<int64_t>(i) * n_units;
-    if (w >= static_cast<int64_t>(a.n_tiles_work) * a.nqc) return false;
-    t = static_cast<int>(w / a.nqc);
-    c = static_cast<int>(w % a.nqc);
-    return true;
+    const int upc = n_units / a.nqc;  // units per chunk (the launcher makes n_units a multiple of nqc)
+    c = unit % a.nqc;
+    t = unit / a.nqc + i * upc;
+    return t < a.n_tiles_work;
 }
 
 // ---- float <-> order-preserving uint32 ------------------------------------------------------
@@ -319,6 +317,11 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int half = (warp - 2) >> 2;     // which 128 of the tile's 256 columns
         const int lane_q = static_cast<int>(cta_rank) * kBM + quad * 32 + lane;  // query inside the chunk
         const uint32_t lead_tempty0 = CG == 2 ? ptx::map_to_cta(ptx::smem_u32(&tempty[0]), 0) : 0;
+        // MAIN: this thread's private candidate segment (no atomics: one writer per segment)
+        const int seg = (unit / a.nqc) * 2 + half;
+        const int my_q = (unit % a.nqc) * kChunk + lane_q;
+        uint64_t* const my_cand = a.cand + (static_cast<size_t>(my_q) * a.n_seg + seg) * a.cap_seg;
+        uint32_t n_admitted = 0;
         int t, c;
         for (int i = 0; get_item(a, unit, n_units, i, t, c); ++i) {
             const uint32_t item = static_cast<uint32_t>(i);
@@ -367,24 +370,23 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
                 for (int i2 = 1; i2 < 32; ++i2) mx = fmaxf(mx, __uint_as_float(v[i2]));
                 // Slow path, taken only when the chunk holds an admitted row: branch-free mask of
-                // the admitted columns, ONE atomicAdd per lane for all of them (the warp's lanes
-                // issue theirs together: one round trip per chunk instead of one per admitted
-                // row — the per-row form made the epilogue the bottleneck on small shards, where
-                // admitted rows are dense; profiles/README.md), then predicated stores.
+                // the admitted columns, then predicated stores into the thread's PRIVATE segment of
+                // the query's candidate buffer — no atomics: with one shared counter per query the
+                // L2 round trip of its atomicAdd stalled the warp ~1 us per chunk, and a warp takes
+                // this path whenever ANY of its 32 queries admits a row (93 % of the chunks of the
+                // RelatedTerms shape, 19 % at 10M rows; profiles/README.md).
                 if (mx >= tau) {
                     uint32_t mask = 0;
 #pragma unroll
                     for (int i2 = 0; i2 < 32; ++i2)
                         mask |= (__uint_as_float(v[i2]) >= tau && i2 < nvalid) ? (1u << i2) : 0u;
                     if (a.row_mask) mask &= a.row_mask[rbase >> 5];
-                    const uint32_t cnt = __popc(mask);
-                    uint32_t slot = cnt ? atomicAdd(&a.cand_count[q], cnt) : 0u;
-                    uint64_t* dst = a.cand + static_cast<size_t>(q) * a.capg;
 #pragma unroll
                     for (int i2 = 0; i2 < 32; ++i2) {
                         if ((mask >> i2) & 1u) {
-                            if (slot < a.capg) dst[slot] = (static_cast<uint64_t>(v[i2]) << 32) | (rbase + i2);
-                            ++slot;
+                            if (n_admitted < a.cap_seg)
+                                my_cand[n_admitted] = (static_cast<uint64_t>(v[i2]) << 32) | (rbase + i2);
+                            ++n_admitted;
                         }
                     }
                 }
@@ -429,6 +431,8 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 a.sample_max[(static_cast<size_t>(t) * 2 + half) * a.nq_pad + q] = bmax;
         }
         if (MODE == kSample) __threadfence();  // block maxima visible device-wide before the unit signs off
+        if (MODE == kMain && unit / a.nqc < n_units / a.nqc)
+            a.cand_count[static_cast<size_t>(my_q) * a.n_seg + seg] = n_admitted;
     }
 
     // teardown: nobody may leave while the peer still reads its smem / signals its barriers
@@ -467,8 +471,17 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             float top[kSampleTop];
 #pragma unroll
             for (int i = 0; i < kSampleTop; ++i) top[i] = -INFINITY;
-            for (int b = part; b < n_blocks; b += 2)
-                insert_top(top, __ldcg(&a.sample_max[static_cast<size_t>(b) * a.nq_pad + q]));
+            // 8 independent loads in flight per thread (a rolled loop pays one L2 latency per block)
+            for (int b0 = part; b0 < n_blocks; b0 += 16) {
+                float x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int b = b0 + 2 * u;
+                    x[u] = b < n_blocks ? __ldcg(&a.sample_max[static_cast<size_t>(b) * a.nq_pad + q]) : -INFINITY;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) insert_top(top, x[u]);
+            }
             if (part == 1) {
 #pragma unroll
                 for (int i = 0; i < kSampleTop; ++i) scratch[(i * kBM) + ql] = top[i];
@@ -487,7 +500,6 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     }
                     a.thr[q] = thr;
                     a.floor_x[q] = floor_x;
-                    a.cand_count[q] = 0;
                     a.retry[q] = 0;
                 }
             }
@@ -502,12 +514,11 @@ __device__ __forceinline__ void store_rn(__half* p, float v) { *p = __float2half
 // per-query state of a search that runs WITHOUT a sample pass (small corpora): the admission
 // threshold is the caller's min_score itself; counters and flags cleared
 __device__ __forceinline__ void init_query_state(int q, int nq, float floor_score, float* thr, float* floor_out,
-                                                 uint32_t* cand_count, int32_t* retry) {
+                                                 int32_t* retry) {
     if (q >= nq) return;
     const float floor_x = dot_floor_for_score(floor_score);
     thr[q] = floor_x;
     floor_out[q] = floor_x;
-    cand_count[q] = 0;
     retry[q] = 0;
 }
 
@@ -515,8 +526,7 @@ __device__ __forceinline__ void init_query_state(int q, int nq, float floor_scor
 // also the per-query search state (see init_query_state) — one launch instead of two
 template <typename T>
 __global__ void query_prep_kernel(const float* q, T* out, int nq, int nq_pad, int dim, int init_state,
-                                  float floor_score, float* thr, float* floor_out, uint32_t* cand_count,
-                                  int32_t* retry) {
+                                  float floor_score, float* thr, float* floor_out, int32_t* retry) {
     const int64_t total = static_cast<int64_t>(nq_pad) * dim;
     const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     for (int64_t i = tid; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -524,7 +534,7 @@ __global__ void query_prep_kernel(const float* q, T* out, int nq, int nq_pad, in
         const float v = row < nq ? q[i] : 0.0f;
         store_rn(out + i, v);
     }
-    if (init_state && tid < nq) init_query_state(static_cast<int>(tid), nq, floor_score, thr, floor_out, cand_count, retry);
+    if (init_state && tid < nq) init_query_state(static_cast<int>(tid), nq, floor_score, thr, floor_out, retry);
 }
 
 // float32 x -> fp16 planes hi = fp16(x), lo = fp16((x - hi) * 2048): x ~= hi + lo / 2048 to 2^-22.
@@ -532,7 +542,7 @@ __global__ void query_prep_kernel(const float* q, T* out, int nq, int nq_pad, in
 // that is not sets *overflow and the caller redoes the search with the exact row scan.
 __global__ void split_rows_kernel(const float* src, __half* hi, __half* lo, int64_t n_valid, int64_t n_total,
                                   int dim, int* overflow, int init_state, float floor_score, float* thr,
-                                  float* floor_out, uint32_t* cand_count, int32_t* retry) {
+                                  float* floor_out, int32_t* retry) {
     const int64_t total = n_total * dim;
     const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     bool bad = false;
@@ -546,21 +556,48 @@ __global__ void split_rows_kernel(const float* src, __half* hi, __half* lo, int6
     }
     if (bad) atomicOr(overflow, 1);
     if (init_state && tid < n_valid)
-        init_query_state(static_cast<int>(tid), static_cast<int>(n_valid), floor_score, thr, floor_out, cand_count, retry);
+        init_query_state(static_cast<int>(tid), static_cast<int>(n_valid), floor_score, thr, floor_out, retry);
 }
 
-// one CTA per query: admitted (dot,row) pairs -> scores -> top-k, or flag the query for the row scan
+// one CTA per query: admitted (dot,row) pairs -> scores -> top-k, or flag the query for the row scan.
+// The candidates of a query lie in n_seg private segments (one per epilogue thread that served it).
 __global__ void __launch_bounds__(kSelectThreads)
-finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t capg, const float* thr,
+finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, int n_seg, uint32_t cap_seg, const float* thr,
                 const float* floor_x, int k, int64_t item_offset, int64_t* out_items, float* out_scores,
                 int32_t* out_counts, int32_t* retry, int32_t* retry_total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
-    __shared__ int s_cnt;
+    __shared__ uint32_t s_prefix[kMaxSegments + 1];
+    __shared__ int s_cnt, s_overflow;
     __shared__ uint64_t s_admit;
     const int q = blockIdx.x, tid = threadIdx.x;
-    const uint32_t total = cand_count[q];
-    const bool overflow = total > capg;
+    const uint32_t* counts = cand_count + static_cast<size_t>(q) * n_seg;
+    if (tid == 0) s_overflow = 0;
+    __syncthreads();
+    for (int sgm = tid; sgm < n_seg; sgm += kSelectThreads) {
+        const uint32_t c = __ldcg(&counts[sgm]);
+        s_prefix[sgm + 1] = c;
+        if (c > cap_seg) s_overflow = 1;
+    }
+    __syncthreads();
+    if (tid < 32) {  // inclusive scan of the segment counts by one warp
+        uint32_t carry = 0;
+        for (int base = 0; base < n_seg; base += 32) {
+            const int i = base + tid;
+            uint32_t v = i < n_seg ? s_prefix[i + 1] : 0u;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, off);
+                if (tid >= off) v += o;
+            }
+            if (i < n_seg) s_prefix[i + 1] = v + carry;
+            carry += __shfl_sync(0xFFFFFFFFu, v, 31);
+        }
+        if (tid == 0) s_prefix[0] = 0;
+    }
+    __syncthreads();
+    const uint32_t total = s_prefix[n_seg];
+    const bool overflow = s_overflow != 0;
     const bool starved = total < static_cast<uint32_t>(k) && thr[q] > floor_x[q];
     int64_t* items = out_items + static_cast<size_t>(q) * k;
     float* scores = out_scores + static_cast<size_t>(q) * k;
@@ -576,23 +613,26 @@ finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t capg,
         }
         return;
     }
-    const uint64_t* in = cand + static_cast<size_t>(q) * capg;
+    const uint64_t* in = cand + static_cast<size_t>(q) * n_seg * cap_seg;
+    auto load_key = [&](int sgm, uint32_t i) {
+        const uint64_t e = __ldcs(&in[static_cast<size_t>(sgm) * cap_seg + i]);
+        return make_key(score_from_dot(__uint_as_float(static_cast<uint32_t>(e >> 32))), static_cast<uint32_t>(e));
+    };
     int n;
     if (total <= static_cast<uint32_t>(kFinalizeFast)) {
-        // the usual case (~`target` admitted rows): everything into shared memory, ONE bitonic sort
+        // the usual case (~`target` admitted rows): everything into shared memory, ONE bitonic sort;
+        // a thread per segment keeps all of a segment's loads in flight
         int cap = 32;
         while (cap < static_cast<int>(total)) cap <<= 1;
-        for (int i = tid; i < cap; i += kSelectThreads) {
-            uint64_t key = 0;
-            if (i < static_cast<int>(total)) {
-                const uint64_t e = __ldcs(&in[i]);
-                key = make_key(score_from_dot(__uint_as_float(static_cast<uint32_t>(e >> 32))), static_cast<uint32_t>(e));
-            }
-            keys[i] = key;
+        for (int i = static_cast<int>(total) + tid; i < cap; i += kSelectThreads) keys[i] = 0;
+        for (int sgm = tid; sgm < n_seg; sgm += kSelectThreads) {
+            const uint32_t base = s_prefix[sgm], cnt = s_prefix[sgm + 1] - base;
+            for (uint32_t i = 0; i < cnt; ++i) keys[base + i] = load_key(sgm, i);
         }
         bitonic_sort_desc<kSelectThreads>(keys, cap);
         n = min(static_cast<int>(total), k);
     } else {
+        // many candidates (large k): stream them through a k-best list with periodic compaction
         const int cap = 1 << (32 - __clz(k + kSelectThreads - 1));
         if (tid == 0) {
             s_cnt = 0;
@@ -605,14 +645,18 @@ finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t capg,
                 need = 0;
                 list_compact<kSelectThreads>(l, cap, k, 0);
             }
-            const uint32_t i = base + tid;
+            const uint32_t e = base + tid;
             uint64_t key = 0;
-            if (i < total) {
-                const uint64_t e = in[i];
-                const float x = __uint_as_float(static_cast<uint32_t>(e >> 32));
-                key = make_key(score_from_dot(x), static_cast<uint32_t>(e));
+            if (e < total) {
+                int lo = 0, hi = n_seg - 1;  // segment holding flat element e: last sgm with prefix[sgm] <= e
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_prefix[mid] <= e) lo = mid;
+                    else hi = mid - 1;
+                }
+                key = load_key(lo, e - s_prefix[lo]);
             }
-            need |= list_push_warp(l, key, i < total && key >= s_admit, cap - kSelectThreads);
+            need |= list_push_warp(l, key, e < total && key >= s_admit, cap - kSelectThreads);
         }
         __syncthreads();
         list_compact<kSelectThreads>(l, cap, k, 0);
@@ -673,8 +717,9 @@ struct Plan {
     int kb_count;
     int n_sample;      // tiles in the sample pass (0 = no sampling)
     int sample_units;  // a multiple of nqc
-    int main_units;
-    uint32_t capg;
+    int main_units;    // a multiple of nqc
+    int n_seg;         // candidate segments per query = 2 * main_units / nqc
+    uint32_t cap_seg;  // rows a segment holds
     // workspace offsets
     size_t off_q, off_q_lo, off_sample, off_thr, off_floor, off_count, off_done, off_cand, total;
 };
@@ -701,22 +746,32 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
     // row scan.  Large corpora aim at 2048 rows, small ones at 128; never fewer than 16k.
     const int64_t target = std::max<int64_t>(
         16ll * k, std::min<int64_t>(2048, std::max<int64_t>(128, n_rows / 4096)));
+    int64_t admitted = n_rows;  // rows a query is expected to admit
     if (n_rows <= 16384 || 8 * target >= n_rows || p.n_full_tiles < 8) {
         p.n_sample = 0;
-        p.capg = static_cast<uint32_t>(n_rows);
     } else {
         const double prob = static_cast<double>(target) / static_cast<double>(n_rows);
         const double q_b = 1.0 - pow(1.0 - prob, 128.0);
         const int64_t blocks = static_cast<int64_t>(ceil(kSampleTop / q_b));
         p.n_sample = static_cast<int>(std::min<int64_t>(p.n_full_tiles, std::max<int64_t>(4, (blocks + 1) / 2)));
-        p.capg = static_cast<uint32_t>(8 * target);
+        admitted = target;
     }
     // sample units: chunk-bound (unit u serves chunk u % nqc), so a multiple of nqc
     {
         const int per_chunk = std::max(1, std::min(std::max(1, max_units / p.nqc), std::max(1, p.n_sample)));
         p.sample_units = per_chunk * p.nqc;  // may exceed max_units when nqc > max_units: extra units queue
     }
-    p.main_units = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(p.n_tiles) * p.nqc, max_units));
+    {
+        // every unit of a chunk owns two candidate segments per query (one per epilogue column half):
+        // room for 16x the expected share of a segment, and for every row it can see when nothing is cut
+        const int per_chunk = std::max(1, std::min(std::max(1, max_units / p.nqc), p.n_tiles));
+        p.main_units = per_chunk * p.nqc;
+        p.n_seg = 2 * per_chunk;
+        const int64_t tiles_per_unit = (p.n_tiles + per_chunk - 1) / per_chunk;
+        const int64_t seen = tiles_per_unit * (kBN / 2);
+        const int64_t want = p.n_sample == 0 ? seen : std::max<int64_t>(64, (16 * admitted + p.n_seg - 1) / p.n_seg);
+        p.cap_seg = static_cast<uint32_t>(std::min<int64_t>(want, seen));
+    }
     auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
     // the sampler's self-resetting unit counters live at a FIXED place (offset 0), whatever the shape of
     // the search: they must read zero at the start of every search and only the kernels ever write them
@@ -734,9 +789,9 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
     p.off_floor = off;
     off = align(off + static_cast<size_t>(p.nq_pad) * sizeof(float));
     p.off_count = off;
-    off = align(off + static_cast<size_t>(p.nq_pad) * sizeof(uint32_t));
+    off = align(off + static_cast<size_t>(p.nq_pad) * p.n_seg * sizeof(uint32_t));
     p.off_cand = off;
-    off = align(off + static_cast<size_t>(p.nq_pad) * p.capg * sizeof(uint64_t));
+    off = align(off + static_cast<size_t>(p.nq_pad) * p.n_seg * p.cap_seg * sizeof(uint64_t));
     p.total = off;
     return p;
 }
@@ -783,24 +838,23 @@ cudaError_t launch_kernel(const Maps& m, const KernelArgs& ka, int cg, int dtype
 }
 
 cudaError_t prep_queries(const MmaArgs& a, void* dst, void* dst_lo, int nq_pad, int init_state, float* thr,
-                         float* floor_out, uint32_t* cand_count, cudaStream_t s) {
+                         float* floor_out, cudaStream_t s) {
     const int64_t total = static_cast<int64_t>(nq_pad) * a.dim;
     const int grid = static_cast<int>(std::max<int64_t>(
         std::min<int64_t>((total + 255) / 256, 148 * 8), init_state ? (a.nq + 255) / 256 : 1));
     if (a.split) {
         split_rows_kernel<<<grid, 256, 0, s>>>(a.queries, static_cast<__half*>(dst), static_cast<__half*>(dst_lo),
                                                a.nq, nq_pad, a.dim, a.split_overflow, init_state, a.floor_score, thr,
-                                               floor_out, cand_count, a.retry_flags);
+                                               floor_out, a.retry_flags);
         return cudaGetLastError();
     }
     if (a.dtype == TAV_BF16)
         query_prep_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(a.queries, static_cast<__nv_bfloat16*>(dst), a.nq, nq_pad,
                                                               a.dim, init_state, a.floor_score, thr, floor_out,
-                                                              cand_count, a.retry_flags);
+                                                              a.retry_flags);
     else
         query_prep_kernel<__half><<<grid, 256, 0, s>>>(a.queries, static_cast<__half*>(dst), a.nq, nq_pad, a.dim,
-                                                       init_state, a.floor_score, thr, floor_out, cand_count,
-                                                       a.retry_flags);
+                                                       init_state, a.floor_score, thr, floor_out, a.retry_flags);
     return cudaGetLastError();
 }
 
@@ -817,7 +871,7 @@ cudaError_t launch_split_rows(const float* src, void* hi, void* lo, int64_t n, i
     const int64_t total = n * dim;
     const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));
     split_rows_kernel<<<grid, 256, 0, s>>>(src, static_cast<__half*>(hi), static_cast<__half*>(lo), n, n, dim, overflow,
-                                           0, 0.0f, nullptr, nullptr, nullptr, nullptr);
+                                           0, 0.0f, nullptr, nullptr, nullptr);
     return cudaGetLastError();
 }
 
@@ -871,7 +925,7 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
 
     // queries -> storage dtype; without a sample pass this launch also initialises thresholds / counters
     if ((e = ev_begin()) != cudaSuccess) return e;
-    e = prep_queries(a, d_q, d_q_lo, p.nq_pad, p.n_sample == 0 ? 1 : 0, d_thr, d_floor, d_count, s);
+    e = prep_queries(a, d_q, d_q_lo, p.nq_pad, p.n_sample == 0 ? 1 : 0, d_thr, d_floor, s);
     if (e != cudaSuccess) return e;
     if ((e = ev_end(2)) != cudaSuccess) return e;
     ++n_launch;
@@ -895,7 +949,8 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
     ka.floor_score = a.floor_score;
     ka.cand = d_cand;
     ka.cand_count = d_count;
-    ka.capg = p.capg;
+    ka.cap_seg = p.cap_seg;
+    ka.n_seg = p.n_seg;
     ka.row_mask = a.row_mask;
 
     if (p.n_sample > 0) {
@@ -903,7 +958,6 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
         ka.n_tiles_work = p.n_sample;
         ka.tile_mul = p.n_full_tiles;
         ka.tile_div = p.n_sample;
-        ka.chunk_bound = 1;
         if ((e = ev_begin()) != cudaSuccess) return e;
         e = launch_kernel<kSample>(maps, ka, p.cg, kdt, split, p.sample_units, s);
         if (e != cudaSuccess) return e;
@@ -914,7 +968,6 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
     ka.n_tiles_work = p.n_tiles;
     ka.tile_mul = 1;
     ka.tile_div = 1;
-    ka.chunk_bound = 0;
     if ((e = ev_begin()) != cudaSuccess) return e;
     e = launch_kernel<kMain>(maps, ka, p.cg, kdt, split, p.main_units, s);
     if (e != cudaSuccess) return e;
@@ -927,9 +980,9 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
     e = ensure_dynamic_smem(finalize_kernel, sel_smem, finalize_granted);
     if (e != cudaSuccess) return e;
     if ((e = ev_begin()) != cudaSuccess) return e;
-    finalize_kernel<<<a.nq, kSelectThreads, sel_smem, s>>>(d_cand, d_count, p.capg, d_thr, d_floor, a.k, a.item_offset,
-                                                           a.out_items, a.out_scores, a.out_counts, a.retry_flags,
-                                                           a.retry_total);
+    finalize_kernel<<<a.nq, kSelectThreads, sel_smem, s>>>(d_cand, d_count, p.n_seg, p.cap_seg, d_thr, d_floor, a.k,
+                                                           a.item_offset, a.out_items, a.out_scores, a.out_counts,
+                                                           a.retry_flags, a.retry_total);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = ev_end(2)) != cudaSuccess) return e;
     ++n_launch;
@@ -947,7 +1000,7 @@ cudaError_t launch_mma_dump(const MmaArgs& a, void* workspace, size_t workspace_
     char* ws = static_cast<char*>(workspace);
     void* d_q = ws + p.off_q;
     void* d_q_lo = ws + p.off_q_lo;
-    cudaError_t e = prep_queries(a, d_q, d_q_lo, p.nq_pad, 0, nullptr, nullptr, nullptr, s);
+    cudaError_t e = prep_queries(a, d_q, d_q_lo, p.nq_pad, 0, nullptr, nullptr, s);
     if (e != cudaSuccess) return e;
     Maps maps;
     if (!build_maps(a, d_q, d_q_lo, p.nq_pad, maps)) return cudaErrorUnknown;

@@ -5,13 +5,21 @@ Reference behaviour being scaled out: ``VectorBase.fuzzy_lookup_embedding`` (/ro
 src/typeagent/aitools/vectorbase.py:163-201) over the *whole* corpus.  Top-k is a decomposable
 reduction, so every rank runs the single-GPU search on its rows (ordinals shifted to global
 rows by ``item_offset``) and the per-rank ``[B, k]`` candidate lists — packed into one buffer —
-are exchanged with ONE ``all_gather_into_tensor`` (NCCL over NVLink / NVSwitch; ~1 MB per rank
-at B=1024, k=100: latency-bound, so a flat gather is optimal) and merged on every rank by
-``tav_merge_topk``.  Result: identical to the unsharded search, including tie order.
+are exchanged and merged on every rank.  Result: identical to the unsharded search, including
+tie order.
 
-``torch`` is plumbing here (process group, device buffers for the collective); the search and
-merge are libtavec kernels.  The engine is injectable so that the host logic (partitioning,
-packing, gather, offsets) is testable on CPU with the ``gloo`` backend.
+Two exchanges:
+  * ``exchange="peer"`` (default on CUDA): libtavec's own (``tav_sharded_search``, csrc/tav_group.cu) —
+    every rank's publish kernel stores its list straight into every peer's HBM over NVLink (CUDA IPC
+    mapped exchange regions, system-scope release flags), the merge waits on the flags; no NCCL call,
+    no host synchronisation, two tiny launches after the local search.  ``torch.distributed`` only
+    carries the 64-byte IPC handles once;
+  * ``exchange="nccl"``: ONE ``all_gather_into_tensor`` + ``tav_merge_topk`` (also what the CPU tests
+    drive over ``gloo`` with an injected engine).
+
+``torch`` is plumbing here (process group, device buffers); the search, exchange and merge are
+libtavec kernels.  The engine is injectable so that the host logic (partitioning, packing, gather,
+offsets) is testable on CPU with the ``gloo`` backend.
 """
 
 from __future__ import annotations
@@ -49,6 +57,78 @@ class CudaShardEngine:
         self.torch = torch
         self.device = torch.device("cuda", device)
         self.base = VectorBase(settings, device=device, storage_dtype=storage_dtype)
+        self._group = None        # tav_group handle (peer exchange)
+        self._group_keep = []     # outputs of deferred group searches, alive until finish
+
+    # ---- peer exchange (tav_group) --------------------------------------------------------
+    GROUP_DEPTH = 8
+
+    def _ensure_group(self, dist, process_group, rank: int, world: int, n_queries: int, k: int):
+        """(Re)create this rank's exchange region when the batch shape outgrows it — collectively:
+        every rank calls with the same shape, the IPC handles travel through all_gather_object."""
+        lib = _capi.load()
+        if self._group is not None:
+            mq, mk = C.c_int(0), C.c_int(0)
+            _capi.check(lib.tav_group_capacity(self._group, C.byref(mq), C.byref(mk), None))
+            if n_queries <= mq.value and k <= mk.value:
+                return self._group
+            self.group_finish()
+            self.torch.cuda.synchronize(self.device)
+            dist.barrier(group=process_group)       # nobody still publishes into a region about to die
+            _capi.check(lib.tav_group_destroy(self._group))
+            self._group = None
+        handle = C.c_void_p()
+        cap_q = max(256, 1 << (max(n_queries, 1) - 1).bit_length())
+        cap_k = max(16, 1 << (max(k, 1) - 1).bit_length())
+        _capi.check(lib.tav_group_create(self.device.index, rank, world, cap_q, cap_k, self.GROUP_DEPTH,
+                                         C.byref(handle)))
+        nbytes = lib.tav_group_handle_bytes()
+        mine = C.create_string_buffer(nbytes)
+        _capi.check(lib.tav_group_local_handle(handle, mine))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bytes(mine.raw), group=process_group)
+        _capi.check(lib.tav_group_connect(handle, b"".join(gathered)))
+        dist.barrier(group=process_group)
+        self._group = handle
+        return handle
+
+    def group_search(self, dist, process_group, rank, world, queries, k, min_score, item_offset, defer_check):
+        torch = self.torch
+        if isinstance(queries, np.ndarray):
+            queries = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).to(self.device, non_blocking=True)
+        b = queries.shape[0]
+        group = self._ensure_group(dist, process_group, rank, world, b, k)
+        lib, ix = self.base._ensure_device()
+        items = torch.empty((b, k), dtype=torch.int64, device=self.device)
+        scores = torch.empty((b, k), dtype=torch.float32, device=self.device)
+        counts = torch.empty((b,), dtype=torch.int32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        flags = self.base._flags() | (_capi.TAV_DEFER_RETRY if defer_check else 0)
+        _capi.check(lib.tav_sharded_search(ix, group, C.c_void_p(queries.data_ptr()), b, k, C.c_float(min_score), flags,
+                                           item_offset, C.c_void_p(items.data_ptr()), C.c_void_p(scores.data_ptr()),
+                                           C.c_void_p(counts.data_ptr()), C.c_void_p(stream)))
+        if defer_check:
+            self._group_keep.append((queries, items, scores, counts, stream))
+        return items, scores, counts
+
+    def group_finish(self) -> int:
+        if self._group is None or not self._group_keep:
+            return 0
+        stream = self._group_keep[-1][4]
+        redone = C.c_int(0)
+        try:
+            _capi.check(_capi.load().tav_sharded_finish(self.base._ix, self._group, C.c_void_p(stream), C.byref(redone)))
+        finally:
+            self._group_keep.clear()
+        return redone.value
+
+    def __del__(self):
+        try:
+            if self._group is not None:
+                _capi.load().tav_group_destroy(self._group)
+                self._group = None
+        except Exception:
+            pass
 
     def comm_device(self):
         return self.device
@@ -113,9 +193,13 @@ class ShardedVectorBase:
     process group.  Every rank calls every method with the same arguments (SPMD)."""
 
     def __init__(self, settings: TextEmbeddingIndexSettings, *, process_group=None,
-                 device: int | None = None, storage_dtype: str = "float32", engine=None):
+                 device: int | None = None, storage_dtype: str = "float32", engine=None,
+                 exchange: str = "peer"):
         import torch.distributed as dist
 
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        self.exchange = exchange
         self.settings = settings
         self._dist = dist
         self._group = process_group
@@ -212,6 +296,11 @@ class ShardedVectorBase:
         b = int(queries.shape[0])
         k = max(1, min(int(k), max(n, 1)))
         lo, _ = self.local_range
+        if self.exchange == "peer" and self.world > 1 and hasattr(self._engine, "group_search"):
+            out = self._engine.group_search(self._dist, self._group, self.rank, self.world, queries, k,
+                                            float(np.float32(min_score)), lo, defer_check)
+            self._pending = ("group",) if defer_check else None
+            return out
         deferrable = hasattr(self._engine, "finish")
         local = (self._engine.search_packed(queries, k, float(np.float32(min_score)), lo, defer_check=True)
                  if deferrable else self._engine.search_packed(queries, k, float(np.float32(min_score)), lo))
@@ -229,6 +318,9 @@ class ShardedVectorBase:
         pending = getattr(self, "_pending", None)
         if pending is None:
             return 0
+        if pending == ("group",):      # libtavec agrees across ranks inside tav_sharded_finish
+            self._pending = None
+            return self._engine.group_finish()
         local, b, k, out = pending
         self._pending = None
         # a local failure must not leave the other ranks waiting in the collective: reduce an error

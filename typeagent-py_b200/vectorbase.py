@@ -26,6 +26,7 @@ every path except the predicate path, which keeps the reference's stable "lower 
 from __future__ import annotations
 
 import ctypes as C
+from array import array as _array
 from collections.abc import Callable, Sequence
 from dataclasses import dataclass
 
@@ -477,18 +478,55 @@ class VectorBase:
             if max_hits == 0:  # the reference's predicate path slices `[:0]` (vectorbase.py:201)
                 return []
             return self._lookup_with_predicate(embedding, k, min_score, predicate)
-        # single-lookup latency path: result buffers are reused across calls (they never escape:
-        # the hits are copied into ScoredInt objects right here)
-        k_eff = max(1, min(k, n))
+        return self._lookup_one(embedding, k, min_score, None)
+
+    def _lookup_one(self, embedding, k: int, min_score: float, subset) -> list[ScoredInt]:
+        """Single-lookup latency path (tools/benchmark_vectorbase.py:97-158 is this call): one host
+        query straight into ``tav_search`` — which serves it with ONE kernel launch, the query riding
+        in the kernel parameters — with reused result buffers and cached ctypes pointers; none of
+        ``search_arrays``' generality (the hits never escape: they are copied into ScoredInt objects)."""
+        q = embedding
+        if not (type(q) is np.ndarray and q.dtype == np.float32 and q.ndim == 1 and q.flags.c_contiguous):
+            q = np.ascontiguousarray(embedding, dtype=np.float32)
+            if q.ndim != 1:
+                q = q.reshape(-1) if q.ndim == 2 and q.shape[0] == 1 else q
+        if q.ndim != 1 or q.shape[0] != self._embedding_size:
+            raise ValueError(
+                f"shapes ({len(self)},{self._embedding_size}) and {tuple(np.shape(embedding))} not aligned"
+            )
+        floor = float(np.float32(min_score))
+        if floor != floor:  # `scores >= nan` is all-false in the reference
+            return []
+        n_rows = len(self)
+        sub_ptr, sub_len, sub = None, 0, None
+        if subset is not None:
+            if type(subset) is list:
+                try:
+                    sub = np.frombuffer(_array("q", subset), dtype=np.int64)   # ~4x faster than np.asarray(list)
+                except (TypeError, OverflowError):
+                    sub = None
+            if sub is None:
+                sub = np.ascontiguousarray(subset)
+                if sub.size and not np.issubdtype(sub.dtype, np.integer):
+                    raise IndexError("arrays used as indices must be of integer (or boolean) type")
+                sub = np.ascontiguousarray(sub.astype(np.int64, copy=False).reshape(-1))
+            n_rows = sub_len = len(sub)
+            sub_ptr = sub.ctypes.data
+        k_eff = max(1, min(k, n_rows))
         out = self._single_out.get(k_eff)
         if out is None:
             if len(self._single_out) > 8:
                 self._single_out.clear()
-            out = self._single_out[k_eff] = (np.empty((1, k_eff), np.int64), np.empty((1, k_eff), np.float32),
-                                             np.empty(1, np.int32))
-        items, scores, counts = self.search_arrays(embedding, k, min_score, out=out)
+            items, scores, counts = np.empty((1, k_eff), np.int64), np.empty((1, k_eff), np.float32), np.empty(1, np.int32)
+            out = self._single_out[k_eff] = (items, scores, counts, items.ctypes.data, scores.ctypes.data,
+                                             counts.ctypes.data)
+        items, scores, counts, ip, sp, cp = out
+        lib, ix = self._ensure_device()
+        rc = lib.tav_search(ix, q.ctypes.data, 1, k_eff, floor, self._flags(), sub_ptr, sub_len, 0, ip, sp, cp, None)
+        if rc < 0:
+            _capi.check(rc)
         c = int(counts[0])
-        return [ScoredInt(i, s) for i, s in zip(items[0, :c].tolist(), scores[0, :c].tolist())]
+        return [ScoredInt(i, s_) for i, s_ in zip(items[0, :c].tolist(), scores[0, :c].tolist())]
 
     _PREDICATE_MASK_ROWS = 65536  # below this many rows the predicate is evaluated up front
 
@@ -547,9 +585,7 @@ class VectorBase:
         if len(ordinals_of_subset) == 0 or len(self) == 0:
             return []
         k = self._resolve_k(max_hits, len(ordinals_of_subset))
-        items, scores, counts = self.search_arrays(embedding, k, min_score, subset=ordinals_of_subset)
-        c = int(counts[0])
-        return [ScoredInt(int(i), float(s)) for i, s in zip(items[0, :c], scores[0, :c])]
+        return self._lookup_one(embedding, k, min_score, ordinals_of_subset)
 
     def fuzzy_lookup_embeddings(
         self,
