@@ -78,7 +78,10 @@ enum tav_search_flags {
     /* Do not use the single-launch form of the row scan (one host query, host outputs: the query
      * rides in the kernel parameters and the last CTA merges); tests use it to reach the two-kernel
      * form with one query. */
-    TAV_NO_FUSED_SCAN = 128
+    TAV_NO_FUSED_SCAN = 128,
+    /* Tensor-core path: keep the query block in shared memory (re-fetched per corpus tile) instead of
+     * parking it in tensor memory; diagnostic / test switch for the Q-stationary form. */
+    TAV_NO_TMEM_QUERIES = 256
 };
 
 int tav_abi_version(void);

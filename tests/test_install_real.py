@@ -183,17 +183,21 @@ def test_reference_built_indexes_return_reference_hits_after_install(name, vecto
         mem, sql = build(vb.TextEmbeddingIndexSettings)       # the reference's code, now on the GPU class
         assert isinstance(mem._vectorbase, tab.VectorBase) and isinstance(sql._vector_base, tab.VectorBase)
         searches = []
-        inner = tab.VectorBase.search_arrays
+        inner, inner_one = tab.VectorBase.search_arrays, tab.VectorBase._lookup_one
 
         def counting(self, *a, **k):
             searches.append(len(np.atleast_2d(a[0])))
             return inner(self, *a, **k)
 
-        tab.VectorBase.search_arrays = counting
+        def counting_one(self, *a, **k):
+            searches.append(1)
+            return inner_one(self, *a, **k)
+
+        tab.VectorBase.search_arrays, tab.VectorBase._lookup_one = counting, counting_one
         try:
             got_mem, got_sql, got_one = asyncio.run(run(mem, sql))
         finally:
-            tab.VectorBase.search_arrays = inner
+            tab.VectorBase.search_arrays, tab.VectorBase._lookup_one = inner, inner_one
     finally:
         tab.uninstall()
     _assert_terms_match(got_mem, want_mem)

@@ -19,7 +19,7 @@ DTYPE_NAMES = {v: k for k, v in DTYPE_CODES.items()}
 
 TAV_NORMALIZE = 1
 TAV_QUERIES_ON_DEVICE, TAV_OUTPUTS_ON_DEVICE, TAV_FORCE_SCAN, TAV_FORCE_MMA, TAV_DEFER_RETRY = 1, 2, 4, 8, 16
-TAV_USE_ROW_MASK, TAV_TIES_LOW_FIRST, TAV_NO_FUSED_SCAN = 32, 64, 128
+TAV_USE_ROW_MASK, TAV_TIES_LOW_FIRST, TAV_NO_FUSED_SCAN, TAV_NO_TMEM_QUERIES = 32, 64, 128, 256
 ABI_VERSION = 2
 
 TAV_ERR_INVALID, TAV_ERR_CUDA, TAV_ERR_OOM, TAV_ERR_RANGE, TAV_ERR_STATE = -1, -2, -3, -4, -5

@@ -90,6 +90,9 @@ constexpr int kMaxPending = 64;        // deferred searches that may await one t
 constexpr size_t kPinnedStageLimit = size_t(8) << 20;  // payloads above this go straight from user memory
 constexpr size_t kZeroCopyOutLimit = size_t(16) << 10; // results up to this size are written to host memory by the kernels
 constexpr size_t kAppendStageBytes = size_t(32) << 20; // pinned double buffer of the bulk-load path
+// the single-launch row scan runs one wave of CTAs (its last CTA merges): a latency form for corpora that
+// fit L2; bigger scans want 4 CTAs per SM in flight and take the two-kernel form
+constexpr size_t kFusedScanMaxBytes = size_t(32) << 20;
 
 // CUDA events around one search (created lazily, when timing is first enabled)
 struct TimedSearch {
@@ -801,6 +804,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
     // raises a completion word the host spins on (tools/benchmark_vectorbase.py:97-158 is this call).
     if (!use_mma && n_queries == 1 && !q_dev && zero_copy_out && !(ix->flags & TAV_NORMALIZE) && k <= 1024 &&
         scan_max_queries(ix->dim, k) >= 1 && scan1_fits(ix->dim, k, n_scan, subset_len, subset != nullptr) &&
+        static_cast<size_t>(n_scan) * ix->dim * dtype_size(ix->dtype) <= kFusedScanMaxBytes &&
         !(flags & TAV_NO_FUSED_SCAN)) {
         ts->path = 1;
         if (int rc = ensure_scan_counters(ix, s)) return rc;
@@ -973,6 +977,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
             m.retry_flags = retry_flags(ix, slot);
             m.retry_total = retry_totals(ix, slot);
             m.row_mask = d_mask;
+            m.no_ts = (flags & TAV_NO_TMEM_QUERIES) ? 1 : 0;
             int ev_used = 0;
             const bool slab_timed = timing && q0 == 0;
             m.ev = slab_timed ? ts->ev : nullptr;
@@ -1071,6 +1076,7 @@ int tav_mma_scores(tav_index* ix, const float* queries, int n_queries, int flags
     m.queries = d_queries;
     m.nq = n_queries;
     m.k = 1;
+    m.no_ts = 1;
     const size_t ws = mma_workspace_bytes(m);
     if (ws > ix->mma_ws.bytes) {
         TAV_CUDA(cudaStreamSynchronize(s));

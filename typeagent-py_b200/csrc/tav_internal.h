@@ -113,6 +113,7 @@ struct MmaArgs {
     int32_t* retry_flags;  // device [nq]: set to 1 for queries the caller must redo with the row scan
     int32_t* retry_total;  // device [1]: incremented once per flagged query (never reset by the kernels)
     const uint32_t* row_mask;  // optional device bitmask over corpus rows (bit set = row may be returned)
+    int no_ts;             // 1: never use the Q-stationary (queries in tensor memory) form
     cudaEvent_t (*ev)[2];  // optional event pairs, one recorded around every kernel launched
     int* ev_kind;          //   kind per pair: 0 = dominant (MAIN) kernel, 1 = sample pass, 2 = auxiliary
     int ev_max;

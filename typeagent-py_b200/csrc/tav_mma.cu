@@ -52,8 +52,10 @@
 
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "tav_common.cuh"
 #include "tav_internal.h"
@@ -79,7 +81,7 @@ constexpr int kMaxChunks = 512;                      // query chunks per launch 
 constexpr int kFinalizeFast = 8192;                 // finalize sorts up to this many candidates in one go
 constexpr int kMaxSegments = 320;                   // candidate segments per query (2 per unit of its chunk)
 // both forms: 192 KB of tiles + barriers + a small scratch used by the sampler's tail
-constexpr size_t kScratchBytes = 2 * 128 * kSampleTop * sizeof(float);
+constexpr size_t kScratchBytes = static_cast<size_t>(kEpiWarps) * 32 * 33 * sizeof(float);  // admit_chunk rows (the sampler tail reuses it)
 constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(4) * kStageBytes + 256 + kScratchBytes;
 
 enum Mode { kSample = 0, kMain = 1, kDump = 2 };
@@ -115,6 +117,51 @@ __device__ __forceinline__ void insert_top(float (&top)[kSampleTop], float x) {
         x = fminf(top[i], x);
         top[i] = hi;
     }
+}
+
+
+// Slow path of the MAIN epilogue, warp-cooperative.  Lane L holds 32 dots of ITS query (a chunk of the
+// tile's rows) and `hit` says whether one of them reaches its admission threshold.  Done lane by lane
+// (branch-free mask + 32 predicated stores, ~300 instructions, executed by the whole warp whenever ANY
+// lane hits) this was the bottleneck of small corpora: at 50k rows a warp hits in 93 % of its chunks.
+// Instead the hit lanes park their 32 values in shared memory (one conflict-free row each) and the warp
+// then walks the hit lanes together: lane j tests value j of lane L against L's threshold, the ballot
+// gives the admitted rows, and they are appended — coalesced — to L's private candidate segment.
+// Must be called convergently by the 32 lanes of a warp; rbase (a multiple of 32) and nvalid are
+// warp-uniform.
+constexpr int kAdmitRow = 33;  // floats per lane row (padded: conflict-free in both directions)
+__device__ __forceinline__ void admit_chunk(const uint32_t (&v)[32], bool hit, float tau, uint32_t rbase, int nvalid,
+                                            const uint32_t* row_mask, float* wscratch, uint64_t* my_cand,
+                                            uint32_t& n_admitted, uint32_t cap_seg, int lane) {
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, hit);
+    if (todo == 0) return;
+    if (hit) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) wscratch[lane * kAdmitRow + i] = __uint_as_float(v[i]);
+    }
+    __syncwarp();
+    uint32_t allowed = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+    if (row_mask) allowed &= row_mask[rbase >> 5];
+    const bool lane_allowed = (allowed >> lane) & 1u;
+    const unsigned long long my_ptr = reinterpret_cast<unsigned long long>(my_cand);
+    while (todo) {
+        const int L = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float x = wscratch[L * kAdmitRow + lane];
+        const float t = __shfl_sync(0xFFFFFFFFu, tau, L);
+        const bool ok = lane_allowed && x >= t;
+        const unsigned bits = __ballot_sync(0xFFFFFFFFu, ok);
+        if (bits) {
+            const uint32_t base = __shfl_sync(0xFFFFFFFFu, n_admitted, L);
+            uint64_t* dst = reinterpret_cast<uint64_t*>(__shfl_sync(0xFFFFFFFFu, my_ptr, L));
+            if (ok) {
+                const uint32_t slot = base + __popc(bits & ((1u << lane) - 1u));
+                if (slot < cap_seg) dst[slot] = (static_cast<uint64_t>(__float_as_uint(x)) << 32) | (rbase + lane);
+            }
+            if (lane == L) n_admitted += __popc(bits);
+        }
+    }
+    __syncwarp();
 }
 
 // Work distribution: unit u (a CTA, or a CTA pair) serves ONE query chunk, c = u % nqc, and every
@@ -322,6 +369,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int my_q = (unit % a.nqc) * kChunk + lane_q;
         uint64_t* const my_cand = a.cand + (static_cast<size_t>(my_q) * a.n_seg + seg) * a.cap_seg;
         uint32_t n_admitted = 0;
+        float* const wscratch = scratch + (warp - 2) * (32 * kAdmitRow);
         int t, c;
         for (int i = 0; get_item(a, unit, n_units, i, t, c); ++i) {
             const uint32_t item = static_cast<uint32_t>(i);
@@ -365,31 +413,14 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     }
                     return;
                 }
-                // MAIN.  Branch-free screen: the chunk's best dot
+                // MAIN.  Branch-free screen: the chunk's best dot; chunks that hold an admitted row take the
+                // warp-cooperative slow path (admit_chunk) into the thread's PRIVATE candidate segment — no
+                // atomics: with one shared counter per query the L2 round trip of its atomicAdd stalled the
+                // warp ~1 us per chunk (profiles/README.md).
                 float mx = __uint_as_float(v[0]);
 #pragma unroll
                 for (int i2 = 1; i2 < 32; ++i2) mx = fmaxf(mx, __uint_as_float(v[i2]));
-                // Slow path, taken only when the chunk holds an admitted row: branch-free mask of
-                // the admitted columns, then predicated stores into the thread's PRIVATE segment of
-                // the query's candidate buffer — no atomics: with one shared counter per query the
-                // L2 round trip of its atomicAdd stalled the warp ~1 us per chunk, and a warp takes
-                // this path whenever ANY of its 32 queries admits a row (93 % of the chunks of the
-                // RelatedTerms shape, 19 % at 10M rows; profiles/README.md).
-                if (mx >= tau) {
-                    uint32_t mask = 0;
-#pragma unroll
-                    for (int i2 = 0; i2 < 32; ++i2)
-                        mask |= (__uint_as_float(v[i2]) >= tau && i2 < nvalid) ? (1u << i2) : 0u;
-                    if (a.row_mask) mask &= a.row_mask[rbase >> 5];
-#pragma unroll
-                    for (int i2 = 0; i2 < 32; ++i2) {
-                        if ((mask >> i2) & 1u) {
-                            if (n_admitted < a.cap_seg)
-                                my_cand[n_admitted] = (static_cast<uint64_t>(v[i2]) << 32) | (rbase + i2);
-                            ++n_admitted;
-                        }
-                    }
-                }
+                admit_chunk(v, mx >= tau, tau, rbase, nvalid, a.row_mask, wscratch, my_cand, n_admitted, a.cap_seg, lane);
             };
 
             uint32_t va[32], vb[32];
@@ -507,6 +538,195 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
 }
 
+// ---- Q-stationary form of the MAIN pass (A operand in tensor memory) ----------------------------
+// For embedding sizes up to 768 the unit's 256 queries fit in TENSOR MEMORY next to the accumulators
+// (128 lanes x D/2 32-bit columns per CTA: 384 columns at D = 768), so they are loaded ONCE per kernel
+// (tcgen05.st) and every MMA takes its A operand from TMEM: the query block is no longer re-fetched
+// from L2 for every corpus tile (that re-fetch doubled the L2 -> SM traffic of the smem-operand form:
+// 30.7 GB per 15.4 GB corpus pass at 10M x 768, profiles/r01_ncu_c3_main_kernel.txt) and shared memory
+// carries the corpus stream alone — a 4-deep ring of whole-K slabs (48 KB per CTA per tile).
+// What is left of TMEM holds two accumulator stages of N = 64 corpus rows (D > 512) or 128 (D <= 512).
+// CTA pairs only (cta_group::2, M = 256 across the pair); same warp roles, candidate segments and
+// exactness argument as mma_topk_kernel<kMain>.
+struct TsArgs {
+    KernelArgs k;
+    const void* q;        // queries in the storage dtype [nq_pad, dim], rows >= nq zero
+    int dim;
+    int tile_n;           // corpus rows per tile across the pair: 64 or 128
+    int n_stages;         // slabs in the shared-memory ring
+    int a_cols;           // TMEM columns holding the query block = kb_count * 32
+};
+
+__global__ void __launch_bounds__(kMmaThreads, 1)
+mma_ts_main_kernel(const __grid_constant__ CUtensorMap map_c, const TsArgs ta, const uint32_t idesc) {
+    const KernelArgs& a = ta.k;
+    constexpr int CG = 2;
+    constexpr int kChunk = kBM * CG;
+    const int rows_cta = ta.tile_n / CG;                       // corpus rows this CTA stages per tile
+    const int kb_bytes = rows_cta * kBK * 2;                   // one 64-wide K slice of the slab
+    const int slab_bytes = kb_bytes * a.kb_count;              // whole-K slab: [kb][rows][64]
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(ta.n_stages) * slab_bytes);
+    uint64_t* full = bars;                 // [8] TMA -> MMA      (the leader's copy is used)
+    uint64_t* empty = bars + 8;            // [8] MMA -> TMA      (each CTA its own)
+    uint64_t* tfull = bars + 16;           // [2] MMA -> epilogue (each CTA its own)
+    uint64_t* tempty = bars + 18;          // [2] epilogue -> MMA (the leader's copy is used)
+    uint64_t* a_full = bars + 20;          // [1] query block resident in TMEM, both CTAs (leader's copy)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = ptx::cluster_ctarank();
+    const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ta.n_stages; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull[s], 1);
+            ptx::mbar_init(&tempty[s], kEpiWarps * CG);
+        }
+        ptx::mbar_init(a_full, kEpiWarps * CG);
+        ptx::fence_mbar_init();
+        ptx::prefetch_tensormap(&map_c);
+    }
+    if (warp == 1) ptx::tmem_alloc_pair(tmem_slot, kTmemCols);
+    ptx::tc_fence_before();
+    ptx::cluster_sync_all();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc_base = tmem_base + static_cast<uint32_t>(ta.a_cols);
+
+    if (warp == 0) {
+        // ================= TMA producer: one whole-K slab of this CTA's rows per tile ==============
+        if (ptx::elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            int t, c;
+            for (int i = 0; get_item(a, unit, n_units, i, t, c); ++i) {
+                const int32_t row0 = t * ta.tile_n + static_cast<int32_t>(cta_rank) * rows_cta;
+                ptx::mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* slab = tiles + static_cast<size_t>(stage) * slab_bytes;
+                const uint32_t lead_full = ptx::map_to_cta(ptx::smem_u32(&full[stage]), 0);
+                if (cta_rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * slab_bytes);
+                for (int kb = 0; kb < a.kb_count; ++kb)
+                    ptx::tma_load_2d_pair(slab + static_cast<size_t>(kb) * kb_bytes, &map_c, lead_full, kb * kBK, row0,
+                                          ptx::kEvictFirst);
+                if (++stage == static_cast<uint32_t>(ta.n_stages)) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA): A from TMEM, B from the slab ===================
+        if (cta_rank == 0 && ptx::elect_one()) {
+            ptx::mbar_wait(a_full, 0);  // both CTAs' query blocks are in tensor memory
+            ptx::tc_fence_after();
+            uint32_t stage = 0, phase = 0;
+            int t, c;
+            for (int i = 0; get_item(a, unit, n_units, i, t, c); ++i) {
+                const uint32_t as = static_cast<uint32_t>(i) & 1u, aphase = (static_cast<uint32_t>(i) >> 1) & 1u;
+                ptx::mbar_wait(&tempty[as], aphase ^ 1);
+                ptx::mbar_wait(&full[stage], phase);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = acc_base + as * static_cast<uint32_t>(ta.tile_n);
+                const uint32_t slab = ptx::smem_u32(tiles + static_cast<size_t>(stage) * slab_bytes);
+                for (int kb = 0; kb < a.kb_count; ++kb) {
+                    const uint64_t db = ptx::make_kmajor_sw128_desc(slab + static_cast<uint32_t>(kb * kb_bytes));
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+                        // 16 K elements = 8 columns of the query block
+                        const uint32_t a_tmem = tmem_base + static_cast<uint32_t>((kb * (kBK / kUmmaK) + k) * (kUmmaK / 2));
+                        ptx::umma_ts_f16_pair(d_tmem, a_tmem, db + koff, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                }
+                ptx::umma_commit_pair(&empty[stage], 3);  // slab reusable (both CTAs) once these MMAs retire
+                ptx::umma_commit_pair(&tfull[as], 3);     // accumulator complete (both CTAs)
+                if (++stage == static_cast<uint32_t>(ta.n_stages)) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warps: first park the query block in TMEM, then screen tiles =====
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int lane_q = static_cast<int>(cta_rank) * kBM + quad * 32 + lane;
+        const int my_q = (unit % a.nqc) * kChunk + lane_q;
+        const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+        const uint32_t lead_tempty0 = ptx::map_to_cta(ptx::smem_u32(&tempty[0]), 0);
+        {
+            // this thread's query row: K slices `half`, half + 2, ... (the two column halves share the work);
+            // one 32-bit column = elements (2c, 2c+1), i.e. the row's bytes in order
+            const uint4* qrow = reinterpret_cast<const uint4*>(static_cast<const char*>(ta.q) +
+                                                               static_cast<size_t>(my_q) * ta.dim * 2);
+            const int n_vec = ta.dim / 8;  // 16-byte vectors in a row (dim % 8 == 0)
+            for (int kb = half; kb < a.kb_count; kb += 2) {
+                uint32_t r[32];
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const int vi = kb * 8 + v;
+                    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                    if (vi < n_vec) x = __ldg(qrow + vi);
+                    r[4 * v + 0] = x.x, r[4 * v + 1] = x.y, r[4 * v + 2] = x.z, r[4 * v + 3] = x.w;
+                }
+                ptx::tmem_st_32x32(tmem_base + lane_addr + static_cast<uint32_t>(kb * 32), r);
+            }
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(a_full), 0));
+        }
+        const int seg = (unit / a.nqc) * 2 + half;
+        uint64_t* const my_cand = a.cand + (static_cast<size_t>(my_q) * a.n_seg + seg) * a.cap_seg;
+        uint32_t n_admitted = 0;
+        float* const wscratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256) + (warp - 2) * (32 * kAdmitRow);
+        const float tau = my_q < a.nq ? a.thr[my_q] : INFINITY;
+        const int cols_warp = ta.tile_n / 2;  // 32 or 64 columns per epilogue warp
+        int t, c;
+        for (int i = 0; get_item(a, unit, n_units, i, t, c); ++i) {
+            const uint32_t as = static_cast<uint32_t>(i) & 1u, aphase = (static_cast<uint32_t>(i) >> 1) & 1u;
+            const int64_t row0 = static_cast<int64_t>(t) * ta.tile_n + half * cols_warp;
+            const int ncols = static_cast<int>(max(static_cast<int64_t>(0),
+                                                   min(static_cast<int64_t>(cols_warp), a.n_rows - row0)));
+            ptx::mbar_wait(&tfull[as], aphase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = acc_base + lane_addr + as * static_cast<uint32_t>(ta.tile_n) +
+                                   static_cast<uint32_t>(half * cols_warp);
+            auto process = [&](const uint32_t (&v)[32], int c0) {
+                const int nvalid = min(32, ncols - c0);
+                const uint32_t rbase = static_cast<uint32_t>(row0 + c0);  // a multiple of 32
+                float mx = __uint_as_float(v[0]);
+#pragma unroll
+                for (int i2 = 1; i2 < 32; ++i2) mx = fmaxf(mx, __uint_as_float(v[i2]));
+                admit_chunk(v, mx >= tau, tau, rbase, nvalid, a.row_mask, wscratch, my_cand, n_admitted, a.cap_seg, lane);
+            };
+            uint32_t va[32], vb[32];
+            if (ncols > 0) ptx::tmem_ld_32x32(taddr, va);
+            if (ncols > 32) ptx::tmem_ld_32x32(taddr + 32, vb);
+            ptx::tmem_ld_wait();
+            // the accumulator is in registers: hand the TMEM stage back before screening
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(lead_tempty0 + as * 8);
+            if (ncols > 0) process(va, 0);
+            if (ncols > 32) process(vb, 32);
+        }
+        if (unit / a.nqc < n_units / a.nqc) a.cand_count[static_cast<size_t>(my_q) * a.n_seg + seg] = n_admitted;
+    }
+
+    ptx::tc_fence_before();
+    ptx::cluster_sync_all();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+    }
+}
+
 // ---- small kernels around the tensor-core passes ---------------------------------------------
 __device__ __forceinline__ void store_rn(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 __device__ __forceinline__ void store_rn(__half* p, float v) { *p = __float2half_rn(v); }
@@ -559,14 +779,107 @@ __global__ void split_rows_kernel(const float* src, __half* hi, __half* lo, int6
         init_query_state(static_cast<int>(tid), static_cast<int>(n_valid), floor_score, thr, floor_out, retry);
 }
 
+// k largest of `total` unsorted keys in shared memory, WITHOUT sorting them all: a histogram of the
+// score bits (kSelBuckets linear buckets between the smallest and the largest score present) locates the
+// bucket that holds the k-th key; keys in higher buckets are certain winners, the boundary bucket is
+// kept whole, and only those (k + a few) keys are sorted.  ~10 CTA barriers instead of the ~80 of a
+// full bitonic sort of 4096 keys.  Returns the number of keys left in `out` (sorted descending, >= k
+// unless total < k), or -1 when the survivors do not fit `out_cap` (massive ties: the caller sorts all).
+constexpr int kSelBuckets = 1024;
+__device__ int select_topk_smem(const uint64_t* keys, int total, int k, uint32_t* hist, uint64_t* out, int out_cap) {
+    __shared__ uint32_t s_lo, s_hi, s_bstar, s_n;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        s_lo = 0xFFFFFFFFu;
+        s_hi = 0u;
+        s_n = 0;
+    }
+    for (int i = tid; i < kSelBuckets; i += kSelectThreads) hist[i] = 0;
+    __syncthreads();
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (int i = tid; i < total; i += kSelectThreads) {
+        const uint32_t sb = static_cast<uint32_t>(keys[i] >> 32);
+        lo = min(lo, sb);
+        hi = max(hi, sb);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, off));
+        hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, off));
+    }
+    if ((tid & 31) == 0) {
+        atomicMin(&s_lo, lo);
+        atomicMax(&s_hi, hi);
+    }
+    __syncthreads();
+    lo = s_lo;
+    const uint64_t span = static_cast<uint64_t>(s_hi - lo) + 1;
+    auto bucket = [&](uint64_t key) {
+        return static_cast<uint32_t>((static_cast<uint64_t>(static_cast<uint32_t>(key >> 32) - lo) * kSelBuckets) / span);
+    };
+    for (int i = tid; i < total; i += kSelectThreads) atomicAdd(&hist[bucket(keys[i])], 1u);
+    __syncthreads();
+    if (tid < 32) {
+        // lane L owns buckets [32L, 32L+32); walk from the top until k keys are covered
+        uint32_t mine = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) mine += hist[tid * 32 + j];
+        uint32_t above = 0;  // keys in the buckets of the lanes above this one (uniform loop: full-mask shuffles)
+        for (int l = 31; l >= 0; --l) {
+            const uint32_t m = __shfl_sync(0xFFFFFFFFu, mine, l);
+            if (l > tid) above += m;
+        }
+        if (above < static_cast<uint32_t>(k) && above + mine >= static_cast<uint32_t>(k)) {
+            uint32_t acc = above;
+            int bsel = tid * 32;
+            for (int j = 31; j >= 0; --j) {
+                acc += hist[tid * 32 + j];
+                if (acc >= static_cast<uint32_t>(k)) {
+                    bsel = tid * 32 + j;
+                    break;
+                }
+            }
+            s_bstar = static_cast<uint32_t>(bsel);
+        }
+        if (tid == 0 && total < k) s_bstar = 0;  // fewer keys than k: keep everything
+    }
+    __syncthreads();
+    const uint32_t bstar = s_bstar;
+    for (int i0 = 0; i0 < total; i0 += kSelectThreads) {
+        const int i = i0 + tid;
+        const uint64_t key = i < total ? keys[i] : 0;
+        const bool keep = i < total && bucket(key) >= bstar;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+        if (m) {
+            uint32_t base = 0;
+            if ((tid & 31) == 0) base = atomicAdd(&s_n, __popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            const uint32_t slot = base + __popc(m & ((1u << (tid & 31)) - 1u));
+            if (keep && slot < static_cast<uint32_t>(out_cap)) out[slot] = key;
+        }
+    }
+    __syncthreads();
+    const int n = static_cast<int>(s_n);
+    if (n > out_cap) return -1;
+    int cap = 32;
+    while (cap < n) cap <<= 1;
+    for (int i = n + tid; i < cap; i += kSelectThreads) out[i] = 0;
+    bitonic_sort_desc<kSelectThreads>(out, cap);
+    return n;
+}
+
 // one CTA per query: admitted (dot,row) pairs -> scores -> top-k, or flag the query for the row scan.
 // The candidates of a query lie in n_seg private segments (one per epilogue thread that served it).
+// Shared memory: [fast_cap keys | kSelOut survivor keys | kSelBuckets histogram words].
+constexpr int kSelOut = 1024;
 __global__ void __launch_bounds__(kSelectThreads)
-finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, int n_seg, uint32_t cap_seg, const float* thr,
-                const float* floor_x, int k, int64_t item_offset, int64_t* out_items, float* out_scores,
-                int32_t* out_counts, int32_t* retry, int32_t* retry_total) {
+finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, int n_seg, uint32_t cap_seg, int fast_cap,
+                const float* thr, const float* floor_x, int k, int64_t item_offset, int64_t* out_items,
+                float* out_scores, int32_t* out_counts, int32_t* retry, int32_t* retry_total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* sel_out = keys + fast_cap;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(sel_out + kSelOut);
     __shared__ uint32_t s_prefix[kMaxSegments + 1];
     __shared__ int s_cnt, s_overflow;
     __shared__ uint64_t s_admit;
@@ -614,23 +927,42 @@ finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, int n_seg, uin
         return;
     }
     const uint64_t* in = cand + static_cast<size_t>(q) * n_seg * cap_seg;
-    auto load_key = [&](int sgm, uint32_t i) {
-        const uint64_t e = __ldcs(&in[static_cast<size_t>(sgm) * cap_seg + i]);
+    auto to_key = [](uint64_t e) {
         return make_key(score_from_dot(__uint_as_float(static_cast<uint32_t>(e >> 32))), static_cast<uint32_t>(e));
     };
     int n;
-    if (total <= static_cast<uint32_t>(kFinalizeFast)) {
-        // the usual case (~`target` admitted rows): everything into shared memory, ONE bitonic sort;
-        // a thread per segment keeps all of a segment's loads in flight
-        int cap = 32;
-        while (cap < static_cast<int>(total)) cap <<= 1;
-        for (int i = static_cast<int>(total) + tid; i < cap; i += kSelectThreads) keys[i] = 0;
+    const uint64_t* result = keys;
+    if (total <= static_cast<uint32_t>(fast_cap)) {
+        // the usual case (~`target` admitted rows): everything into shared memory — a thread per segment,
+        // four independent loads in flight each — then the k best by histogram selection
         for (int sgm = tid; sgm < n_seg; sgm += kSelectThreads) {
             const uint32_t base = s_prefix[sgm], cnt = s_prefix[sgm + 1] - base;
-            for (uint32_t i = 0; i < cnt; ++i) keys[base + i] = load_key(sgm, i);
+            const uint64_t* src = in + static_cast<size_t>(sgm) * cap_seg;
+            for (uint32_t i = 0; i < cnt; i += 4) {
+                uint64_t e[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e[u] = i + u < cnt ? __ldcs(&src[i + u]) : 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i + u < cnt) keys[base + i + u] = to_key(e[u]);
+            }
         }
-        bitonic_sort_desc<kSelectThreads>(keys, cap);
-        n = min(static_cast<int>(total), k);
+        __syncthreads();
+        n = -1;
+        if (k <= kSelOut / 2 && total > 256) {
+            const int got = select_topk_smem(keys, static_cast<int>(total), k, hist, sel_out, kSelOut);
+            if (got >= 0) {
+                n = min(got, k);
+                result = sel_out;
+            }
+        }
+        if (n < 0) {  // few keys, large k, or massive ties: one bitonic sort of everything
+            int cap = 32;
+            while (cap < static_cast<int>(total)) cap <<= 1;
+            for (int i = static_cast<int>(total) + tid; i < cap; i += kSelectThreads) keys[i] = 0;
+            bitonic_sort_desc<kSelectThreads>(keys, cap);
+            n = min(static_cast<int>(total), k);
+        }
     } else {
         // many candidates (large k): stream them through a k-best list with periodic compaction
         const int cap = 1 << (32 - __clz(k + kSelectThreads - 1));
@@ -654,7 +986,7 @@ finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, int n_seg, uin
                     if (s_prefix[mid] <= e) lo = mid;
                     else hi = mid - 1;
                 }
-                key = load_key(lo, e - s_prefix[lo]);
+                key = to_key(__ldcs(&in[static_cast<size_t>(lo) * cap_seg + (e - s_prefix[lo])]));
             }
             need |= list_push_warp(l, key, e < total && key >= s_admit, cap - kSelectThreads);
         }
@@ -664,8 +996,8 @@ finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, int n_seg, uin
     }
     for (int j = tid; j < k; j += kSelectThreads) {
         if (j < n) {
-            items[j] = static_cast<int64_t>(key_pos(keys[j])) + item_offset;
-            scores[j] = key_score(keys[j]);
+            items[j] = static_cast<int64_t>(key_pos(result[j])) + item_offset;
+            scores[j] = key_score(result[j]);
         } else {
             items[j] = -1;
             scores[j] = 0.0f;
@@ -720,11 +1052,21 @@ struct Plan {
     int main_units;    // a multiple of nqc
     int n_seg;         // candidate segments per query = 2 * main_units / nqc
     uint32_t cap_seg;  // rows a segment holds
+    bool ts;           // MAIN runs in the Q-stationary form (query block in tensor memory)
+    int tile_n;        // corpus rows per MAIN tile: 256, or 64 / 128 in the Q-stationary form
+    int n_main_tiles;
+    int ts_stages;     // slabs in the Q-stationary form's shared-memory ring
+    size_t ts_smem;
     // workspace offsets
     size_t off_q, off_q_lo, off_sample, off_thr, off_floor, off_count, off_done, off_cand, total;
 };
 
-Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
+bool ts_enabled() {
+    static const bool on = getenv("TAV_NO_TS") == nullptr;  // diagnostic switch: force the smem-operand form
+    return on;
+}
+
+Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k, bool split, bool no_ts = false) {
     Plan p{};
     p.sms = 148;
     cudaDeviceGetAttribute(&p.sms, cudaDevAttrMultiProcessorCount, device);
@@ -735,6 +1077,16 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
     p.n_tiles = static_cast<int>((n_rows + kBN - 1) / kBN);
     p.n_full_tiles = static_cast<int>(n_rows / kBN);
     p.kb_count = (dim + kBK - 1) / kBK;
+    // Q-stationary MAIN: CTA pairs, 16-bit storage, query block (kb_count * 32 TMEM columns) + two
+    // accumulator stages within the 512 columns of tensor memory
+    p.ts = p.cg == 2 && !split && !no_ts && p.kb_count * 32 <= 384 && ts_enabled();
+    p.tile_n = !p.ts ? kBN : (p.kb_count * 32 > 256 ? 64 : 128);
+    p.n_main_tiles = static_cast<int>((n_rows + p.tile_n - 1) / p.tile_n);
+    if (p.ts) {
+        const size_t slab = static_cast<size_t>(p.tile_n / 2) * kBK * 2 * p.kb_count;
+        p.ts_stages = static_cast<int>(std::max<size_t>(2, std::min<size_t>(8, (200 * 1024) / slab)));
+        p.ts_smem = 1024 + p.ts_stages * slab + 256 + kScratchBytes;
+    }
     const int max_units = p.cg == 2 ? std::max(1, p.sms / 2) : p.sms;
     // Rows we aim to admit per query (`target`).  The threshold is the m-th largest (m = kSampleTop = 8)
     // block maximum of a uniform sample of L blocks of 128 rows; with p = target / N the chance that a
@@ -764,11 +1116,11 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k) {
     {
         // every unit of a chunk owns two candidate segments per query (one per epilogue column half):
         // room for 16x the expected share of a segment, and for every row it can see when nothing is cut
-        const int per_chunk = std::max(1, std::min(std::max(1, max_units / p.nqc), p.n_tiles));
+        const int per_chunk = std::max(1, std::min(std::max(1, max_units / p.nqc), p.n_main_tiles));
         p.main_units = per_chunk * p.nqc;
         p.n_seg = 2 * per_chunk;
-        const int64_t tiles_per_unit = (p.n_tiles + per_chunk - 1) / per_chunk;
-        const int64_t seen = tiles_per_unit * (kBN / 2);
+        const int64_t tiles_per_unit = (p.n_main_tiles + per_chunk - 1) / per_chunk;
+        const int64_t seen = tiles_per_unit * (p.tile_n / 2);
         const int64_t want = p.n_sample == 0 ? seen : std::max<int64_t>(64, (16 * admitted + p.n_seg - 1) / p.n_seg);
         p.cap_seg = static_cast<uint32_t>(std::min<int64_t>(want, seen));
     }
@@ -879,7 +1231,42 @@ namespace {
 // storage dtype the tensor-core kernel sees: fp16 planes for split float32 data
 inline int mma_dtype(const MmaArgs& a) { return a.split ? TAV_F16 : a.dtype; }
 
-bool build_maps(const MmaArgs& a, const void* d_q, const void* d_q_lo, int nq_pad, Maps& m) {
+bool build_maps_uncached(const MmaArgs& a, const void* d_q, const void* d_q_lo, int nq_pad, Maps& m);
+
+// cuTensorMapEncodeTiled costs 1-2 us a piece and a search needs seven: remember, per device, the maps of
+// the last search (serving loops repeat the same corpus / workspace pointers and shapes)
+struct MapCacheEntry {
+    const void *corpus = nullptr, *corpus_lo = nullptr, *q = nullptr, *q_lo = nullptr;
+    int64_t n = -1;
+    int dim = 0, dt = -1, nq_pad = 0, ts_rows = 0;
+    Maps maps;
+    CUtensorMap ts;
+    bool valid = false;
+};
+std::mutex g_map_mu;
+MapCacheEntry g_map_cache[16];
+
+bool build_maps(const MmaArgs& a, const void* d_q, const void* d_q_lo, int nq_pad, int ts_rows, Maps& m,
+                CUtensorMap* ts_map) {
+    const int dt = mma_dtype(a);
+    std::lock_guard<std::mutex> lock(g_map_mu);
+    MapCacheEntry& e = g_map_cache[a.device >= 0 && a.device < 16 ? a.device : 0];
+    const void* lo = a.split ? a.corpus_lo : nullptr;
+    if (!(e.valid && e.corpus == a.corpus && e.corpus_lo == lo && e.q == d_q && e.q_lo == d_q_lo && e.n == a.n_corpus &&
+          e.dim == a.dim && e.dt == dt && e.nq_pad == nq_pad && e.ts_rows == ts_rows)) {
+        e.valid = false;
+        if (!build_maps_uncached(a, d_q, d_q_lo, nq_pad, e.maps)) return false;
+        if (ts_rows > 0 && !encode_map(&e.ts, dt, a.corpus, a.n_corpus, a.dim, ts_rows)) return false;
+        e.corpus = a.corpus, e.corpus_lo = lo, e.q = d_q, e.q_lo = d_q_lo, e.n = a.n_corpus;
+        e.dim = a.dim, e.dt = dt, e.nq_pad = nq_pad, e.ts_rows = ts_rows;
+        e.valid = true;
+    }
+    m = e.maps;
+    if (ts_map && ts_rows > 0) *ts_map = e.ts;
+    return true;
+}
+
+bool build_maps_uncached(const MmaArgs& a, const void* d_q, const void* d_q_lo, int nq_pad, Maps& m) {
     const int dt = mma_dtype(a);
     if (!encode_map(&m.c1, dt, a.corpus, a.n_corpus, a.dim, kBN)) return false;
     if (!encode_map(&m.c2, dt, a.corpus, a.n_corpus, a.dim, kBN / 2)) return false;
@@ -896,12 +1283,14 @@ bool args_ok(const MmaArgs& a) {
 }
 }  // namespace
 
-size_t mma_workspace_bytes(const MmaArgs& a) { return make_plan(a.device, a.n_corpus, a.dim, a.nq, a.k).total; }
+size_t mma_workspace_bytes(const MmaArgs& a) {
+    return make_plan(a.device, a.n_corpus, a.dim, a.nq, a.k, a.split != 0, a.no_ts != 0).total;
+}
 
 cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s,
                               int* launches) {
     if (!args_ok(a) || a.k > kPassK || a.nq < 1 || a.nq > kMmaMaxQueries) return cudaErrorInvalidValue;
-    const Plan p = make_plan(a.device, a.n_corpus, a.dim, a.nq, a.k);
+    const Plan p = make_plan(a.device, a.n_corpus, a.dim, a.nq, a.k, a.split != 0, a.no_ts != 0);
     if (workspace_bytes < p.total) return cudaErrorInvalidValue;
     char* ws = static_cast<char*>(workspace);
     void* d_q = ws + p.off_q;
@@ -923,15 +1312,17 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
         return cudaEventRecord(a.ev[ev_used++][1], s);
     };
 
+    // tensor maps first (host work only), so that the launches below go out back to back
+    Maps maps;
+    CUtensorMap map_ts;
+    if (!build_maps(a, d_q, d_q_lo, p.nq_pad, p.ts ? p.tile_n / 2 : 0, maps, &map_ts)) return cudaErrorUnknown;
+
     // queries -> storage dtype; without a sample pass this launch also initialises thresholds / counters
     if ((e = ev_begin()) != cudaSuccess) return e;
     e = prep_queries(a, d_q, d_q_lo, p.nq_pad, p.n_sample == 0 ? 1 : 0, d_thr, d_floor, s);
     if (e != cudaSuccess) return e;
     if ((e = ev_end(2)) != cudaSuccess) return e;
     ++n_launch;
-
-    Maps maps;
-    if (!build_maps(a, d_q, d_q_lo, p.nq_pad, maps)) return cudaErrorUnknown;
     const int kdt = mma_dtype(a);
     const bool split = a.split != 0;
 
@@ -965,24 +1356,57 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
         ++n_launch;
     }
 
-    ka.n_tiles_work = p.n_tiles;
+    ka.n_tiles_work = p.n_main_tiles;
     ka.tile_mul = 1;
     ka.tile_div = 1;
     if ((e = ev_begin()) != cudaSuccess) return e;
-    e = launch_kernel<kMain>(maps, ka, p.cg, kdt, split, p.main_units, s);
+    if (p.ts) {
+        // Q-stationary form: query block in tensor memory, corpus slabs through shared memory
+        TsArgs ta{};
+        ta.k = ka;
+        ta.q = d_q;
+        ta.dim = a.dim;
+        ta.tile_n = p.tile_n;
+        ta.n_stages = p.ts_stages;
+        ta.a_cols = p.kb_count * 32;
+        static int ts_granted[16] = {};
+        e = ensure_dynamic_smem(mma_ts_main_kernel, p.ts_smem, ts_granted);
+        if (e != cudaSuccess) return e;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(static_cast<unsigned>(p.main_units * 2));
+        cfg.blockDim = dim3(kMmaThreads);
+        cfg.dynamicSmemBytes = p.ts_smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const uint32_t idesc_ts = ptx::make_idesc_f16(2 * kBM, p.tile_n, kdt == TAV_BF16 ? 1 : 0);
+        e = cudaLaunchKernelEx(&cfg, mma_ts_main_kernel, map_ts, ta, idesc_ts);
+    } else {
+        e = launch_kernel<kMain>(maps, ka, p.cg, kdt, split, p.main_units, s);
+    }
     if (e != cudaSuccess) return e;
     if ((e = ev_end(0)) != cudaSuccess) return e;
     ++n_launch;
 
-    const size_t sel_smem =
-        static_cast<size_t>(std::max(kFinalizeFast, next_pow2(a.k + kSelectThreads))) * sizeof(uint64_t);
+    // shared memory sized to what this search can need: all candidates of a query (bounded by the segments'
+    // capacity and kFinalizeFast) or the streaming list for large k, + the selection's survivors and histogram
+    const int64_t most = static_cast<int64_t>(p.n_seg) * p.cap_seg;
+    const int fast_cap = std::max(next_pow2(a.k + kSelectThreads),
+                                  static_cast<int>(std::min<int64_t>(kFinalizeFast, next_pow2(static_cast<int>(std::min<int64_t>(most, kFinalizeFast))))));
+    const size_t sel_smem = static_cast<size_t>(fast_cap) * sizeof(uint64_t) + kSelOut * sizeof(uint64_t) +
+                            kSelBuckets * sizeof(uint32_t);
     static int finalize_granted[16] = {};
     e = ensure_dynamic_smem(finalize_kernel, sel_smem, finalize_granted);
     if (e != cudaSuccess) return e;
     if ((e = ev_begin()) != cudaSuccess) return e;
-    finalize_kernel<<<a.nq, kSelectThreads, sel_smem, s>>>(d_cand, d_count, p.n_seg, p.cap_seg, d_thr, d_floor, a.k,
-                                                           a.item_offset, a.out_items, a.out_scores, a.out_counts,
-                                                           a.retry_flags, a.retry_total);
+    finalize_kernel<<<a.nq, kSelectThreads, sel_smem, s>>>(d_cand, d_count, p.n_seg, p.cap_seg, fast_cap, d_thr, d_floor,
+                                                           a.k, a.item_offset, a.out_items, a.out_scores,
+                                                           a.out_counts, a.retry_flags, a.retry_total);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = ev_end(2)) != cudaSuccess) return e;
     ++n_launch;
@@ -995,7 +1419,7 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
 // Debug / verification entry: all raw dot products of the tensor-core path, out[nq, n_rows] (device).
 cudaError_t launch_mma_dump(const MmaArgs& a, void* workspace, size_t workspace_bytes, float* out, cudaStream_t s) {
     if (!args_ok(a) || a.nq < 1 || a.nq > kMmaMaxQueries) return cudaErrorInvalidValue;
-    const Plan p = make_plan(a.device, a.n_corpus, a.dim, a.nq, 1);
+    Plan p = make_plan(a.device, a.n_corpus, a.dim, a.nq, 1, a.split != 0, true);
     if (workspace_bytes < p.total) return cudaErrorInvalidValue;
     char* ws = static_cast<char*>(workspace);
     void* d_q = ws + p.off_q;
@@ -1003,7 +1427,7 @@ cudaError_t launch_mma_dump(const MmaArgs& a, void* workspace, size_t workspace_
     cudaError_t e = prep_queries(a, d_q, d_q_lo, p.nq_pad, 0, nullptr, nullptr, s);
     if (e != cudaSuccess) return e;
     Maps maps;
-    if (!build_maps(a, d_q, d_q_lo, p.nq_pad, maps)) return cudaErrorUnknown;
+    if (!build_maps(a, d_q, d_q_lo, p.nq_pad, 0, maps, nullptr)) return cudaErrorUnknown;
     KernelArgs ka{};
     ka.n_rows = a.n_corpus;
     ka.kb_count = p.kb_count;

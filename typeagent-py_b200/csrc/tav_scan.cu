@@ -408,7 +408,9 @@ int scan1_grid(int device, int dim, int k, int64_t n_scan) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     int64_t tiles = (n_scan + kRoundRows - 1) / kRoundRows;
-    int64_t g = std::min<int64_t>(tiles, sms);          // one wave: the last CTA's merge stays short
+    // small corpora: one CTA per SM (the last CTA's merge stays short); large ones: up to 4 per SM so that
+    // enough loads are in flight to fill HBM, as long as every CTA still has >= 8 rounds of rows
+    int64_t g = std::min<int64_t>(tiles, std::max<int64_t>(sms, std::min<int64_t>(tiles / 8, 4ll * sms)));
     g = std::min<int64_t>(g, kFusedSelectMax / std::max(k, 1));
     (void)dim;
     return static_cast<int>(std::max<int64_t>(g, 1));

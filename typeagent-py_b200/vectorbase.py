@@ -325,6 +325,8 @@ class VectorBase:
             return _capi.TAV_FORCE_SCAN | _capi.TAV_NO_FUSED_SCAN
         if self.force_path == "mma":
             return _capi.TAV_FORCE_MMA
+        if self.force_path == "mma_smem":   # tensor cores with the query block in shared memory (no TMEM parking)
+            return _capi.TAV_FORCE_MMA | _capi.TAV_NO_TMEM_QUERIES
         return 0
 
     # ------------------------------------------------------------------ row masks
