@@ -61,11 +61,12 @@ def main():
         for _ in range(200):
             base.fuzzy_lookup_embedding(q, 10, 0.0)
             gpu_ms.append(base.last_timing()["scan_ms"])
+        launches = base.last_timing()["launches"]
         base.enable_timing(False)
         gpu_us = sorted(gpu_ms)[len(gpu_ms) // 2] * 1e3
         print(f"{rows}x{dim}: ctypes call {t_size:.1f} us | tav_search (raw ctypes) {t_raw:.1f} us | "
               f"search_arrays {t_arrays:.1f} us | fuzzy_lookup_embedding {t_lookup:.1f} us | in_subset(1000) {t_subset:.1f} us "
-              f"(np.asarray(list) alone {t_aslist:.1f} us) | kernel on the GPU {gpu_us:.1f} us ({base.last_timing()['launches']} "
+              f"(np.asarray(list) alone {t_aslist:.1f} us) | kernel on the GPU {gpu_us:.1f} us ({launches} "
               f"launch) | np.dot alone {t_numpy:.1f} us", flush=True)
 
 

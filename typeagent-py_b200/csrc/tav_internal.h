@@ -38,10 +38,12 @@ struct ScanArgs {
     uint32_t* done_flag;      // mapped pinned host word set to done_seq once the hits are written, or nullptr
     uint32_t done_seq;
 };
-constexpr int kFusedSelectMax = 4096;   // keys the last CTA of the single-launch form sorts at once
+constexpr int kFusedSelectMax = 8192;   // survivors the last CTA of the single-launch form can merge
+constexpr int kFusedSelOut = 1024;      // ... of which it sorts at most this many after the histogram selection
 constexpr int kParamQuerySmall = 1024;  // floats of query carried in a 4 KB kernel-parameter blob
 constexpr int kParamQueryBig = 3072;    // ... in the 28 KB blob (with up to kParamSubsetMax ordinals)
 constexpr int kParamSubsetMax = 4096;
+constexpr int kParamSubsetSmall = 1024; // ordinals in the 8 KB blob (with a query of <= kParamQuerySmall floats)
 bool scan1_fits(int dim, int k, int64_t n_scan, int64_t subset_len, bool has_subset);
 int scan1_grid(int device, int dim, int k, int64_t n_scan);
 // q_host: float32 [dim] on the host; sub_host: int64 [n_scan] validated ordinals or nullptr

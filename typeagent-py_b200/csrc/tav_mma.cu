@@ -633,15 +633,24 @@ mma_ts_main_kernel(const __grid_constant__ CUtensorMap map_c, const TsArgs ta, c
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = acc_base + as * static_cast<uint32_t>(ta.tile_n);
                 const uint32_t slab = ptx::smem_u32(tiles + static_cast<size_t>(stage) * slab_bytes);
-                for (int kb = 0; kb < a.kb_count; ++kb) {
-                    const uint64_t db = ptx::make_kmajor_sw128_desc(slab + static_cast<uint32_t>(kb * kb_bytes));
-#pragma unroll
-                    for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
-                        // 16 K elements = 8 columns of the query block
-                        const uint32_t a_tmem = tmem_base + static_cast<uint32_t>((kb * (kBK / kUmmaK) + k) * (kUmmaK / 2));
-                        ptx::umma_ts_f16_pair(d_tmem, a_tmem, db + koff, idesc, (kb | k) != 0 ? 1u : 0u);
-                    }
+                // one MMA per 16 K elements: B descriptor + 2 (32 bytes >> 4) inside a 64-wide slice, + one
+                // slice per K block; A = 8 more TMEM columns.  Kept to a handful of instructions per MMA: a
+                // single thread has to issue one every 32 tensor-pipe cycles at N = 64.
+                uint64_t db = ptx::make_kmajor_sw128_desc(slab);
+                const uint64_t db_step = static_cast<uint64_t>(kb_bytes >> 4);
+                uint32_t a_tmem = tmem_base;
+                ptx::umma_ts_f16_pair(d_tmem, a_tmem, db, idesc, 0u);
+                ptx::umma_ts_f16_pair(d_tmem, a_tmem + 8, db + 2, idesc, 1u);
+                ptx::umma_ts_f16_pair(d_tmem, a_tmem + 16, db + 4, idesc, 1u);
+                ptx::umma_ts_f16_pair(d_tmem, a_tmem + 24, db + 6, idesc, 1u);
+#pragma unroll 2
+                for (int kb = 1; kb < a.kb_count; ++kb) {
+                    db += db_step;
+                    a_tmem += 32;
+                    ptx::umma_ts_f16_pair(d_tmem, a_tmem, db, idesc, 1u);
+                    ptx::umma_ts_f16_pair(d_tmem, a_tmem + 8, db + 2, idesc, 1u);
+                    ptx::umma_ts_f16_pair(d_tmem, a_tmem + 16, db + 4, idesc, 1u);
+                    ptx::umma_ts_f16_pair(d_tmem, a_tmem + 24, db + 6, idesc, 1u);
                 }
                 ptx::umma_commit_pair(&empty[stage], 3);  // slab reusable (both CTAs) once these MMAs retire
                 ptx::umma_commit_pair(&tfull[as], 3);     // accumulator complete (both CTAs)
@@ -779,95 +788,6 @@ __global__ void split_rows_kernel(const float* src, __half* hi, __half* lo, int6
         init_query_state(static_cast<int>(tid), static_cast<int>(n_valid), floor_score, thr, floor_out, retry);
 }
 
-// k largest of `total` unsorted keys in shared memory, WITHOUT sorting them all: a histogram of the
-// score bits (kSelBuckets linear buckets between the smallest and the largest score present) locates the
-// bucket that holds the k-th key; keys in higher buckets are certain winners, the boundary bucket is
-// kept whole, and only those (k + a few) keys are sorted.  ~10 CTA barriers instead of the ~80 of a
-// full bitonic sort of 4096 keys.  Returns the number of keys left in `out` (sorted descending, >= k
-// unless total < k), or -1 when the survivors do not fit `out_cap` (massive ties: the caller sorts all).
-constexpr int kSelBuckets = 1024;
-__device__ int select_topk_smem(const uint64_t* keys, int total, int k, uint32_t* hist, uint64_t* out, int out_cap) {
-    __shared__ uint32_t s_lo, s_hi, s_bstar, s_n;
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        s_lo = 0xFFFFFFFFu;
-        s_hi = 0u;
-        s_n = 0;
-    }
-    for (int i = tid; i < kSelBuckets; i += kSelectThreads) hist[i] = 0;
-    __syncthreads();
-    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-    for (int i = tid; i < total; i += kSelectThreads) {
-        const uint32_t sb = static_cast<uint32_t>(keys[i] >> 32);
-        lo = min(lo, sb);
-        hi = max(hi, sb);
-    }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, off));
-        hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, off));
-    }
-    if ((tid & 31) == 0) {
-        atomicMin(&s_lo, lo);
-        atomicMax(&s_hi, hi);
-    }
-    __syncthreads();
-    lo = s_lo;
-    const uint64_t span = static_cast<uint64_t>(s_hi - lo) + 1;
-    auto bucket = [&](uint64_t key) {
-        return static_cast<uint32_t>((static_cast<uint64_t>(static_cast<uint32_t>(key >> 32) - lo) * kSelBuckets) / span);
-    };
-    for (int i = tid; i < total; i += kSelectThreads) atomicAdd(&hist[bucket(keys[i])], 1u);
-    __syncthreads();
-    if (tid < 32) {
-        // lane L owns buckets [32L, 32L+32); walk from the top until k keys are covered
-        uint32_t mine = 0;
-#pragma unroll 8
-        for (int j = 0; j < 32; ++j) mine += hist[tid * 32 + j];
-        uint32_t above = 0;  // keys in the buckets of the lanes above this one (uniform loop: full-mask shuffles)
-        for (int l = 31; l >= 0; --l) {
-            const uint32_t m = __shfl_sync(0xFFFFFFFFu, mine, l);
-            if (l > tid) above += m;
-        }
-        if (above < static_cast<uint32_t>(k) && above + mine >= static_cast<uint32_t>(k)) {
-            uint32_t acc = above;
-            int bsel = tid * 32;
-            for (int j = 31; j >= 0; --j) {
-                acc += hist[tid * 32 + j];
-                if (acc >= static_cast<uint32_t>(k)) {
-                    bsel = tid * 32 + j;
-                    break;
-                }
-            }
-            s_bstar = static_cast<uint32_t>(bsel);
-        }
-        if (tid == 0 && total < k) s_bstar = 0;  // fewer keys than k: keep everything
-    }
-    __syncthreads();
-    const uint32_t bstar = s_bstar;
-    for (int i0 = 0; i0 < total; i0 += kSelectThreads) {
-        const int i = i0 + tid;
-        const uint64_t key = i < total ? keys[i] : 0;
-        const bool keep = i < total && bucket(key) >= bstar;
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
-        if (m) {
-            uint32_t base = 0;
-            if ((tid & 31) == 0) base = atomicAdd(&s_n, __popc(m));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            const uint32_t slot = base + __popc(m & ((1u << (tid & 31)) - 1u));
-            if (keep && slot < static_cast<uint32_t>(out_cap)) out[slot] = key;
-        }
-    }
-    __syncthreads();
-    const int n = static_cast<int>(s_n);
-    if (n > out_cap) return -1;
-    int cap = 32;
-    while (cap < n) cap <<= 1;
-    for (int i = n + tid; i < cap; i += kSelectThreads) out[i] = 0;
-    bitonic_sort_desc<kSelectThreads>(out, cap);
-    return n;
-}
-
 // one CTA per query: admitted (dot,row) pairs -> scores -> top-k, or flag the query for the row scan.
 // The candidates of a query lie in n_seg private segments (one per epilogue thread that served it).
 // Shared memory: [fast_cap keys | kSelOut survivor keys | kSelBuckets histogram words].
@@ -950,7 +870,7 @@ finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, int n_seg, uin
         __syncthreads();
         n = -1;
         if (k <= kSelOut / 2 && total > 256) {
-            const int got = select_topk_smem(keys, static_cast<int>(total), k, hist, sel_out, kSelOut);
+            const int got = select_topk_smem<kSelectThreads>(keys, static_cast<int>(total), k, hist, sel_out, kSelOut);
             if (got >= 0) {
                 n = min(got, k);
                 result = sel_out;

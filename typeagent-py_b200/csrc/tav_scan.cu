@@ -36,7 +36,10 @@ static inline int scan_cap(int k) {
 static inline size_t scan_smem_bytes(int qb, int dim, int k, bool fused = false) {
     size_t q_bytes = (static_cast<size_t>(qb) * dim * sizeof(float) + 15) & ~size_t(15);
     size_t lists = static_cast<size_t>(qb) * scan_cap(k) * sizeof(uint64_t);
-    if (fused) lists = std::max(lists, static_cast<size_t>(kFusedSelectMax) * sizeof(uint64_t));
+    // single-launch form: the last CTA's merge needs all survivors + the selection's output and histogram
+    if (fused)
+        lists = std::max(lists, static_cast<size_t>(kFusedSelectMax) * sizeof(uint64_t) + kFusedSelOut * sizeof(uint64_t) +
+                                    kSelBuckets * sizeof(uint32_t));
     return q_bytes + lists;
 }
 
@@ -311,21 +314,37 @@ scan_rows_kernel(const ScanArgs a, const __grid_constant__ BLOB blob) {
             while (cap2 < total) cap2 <<= 1;
             const uint64_t* in = a.cand_keys + static_cast<size_t>(q) * a.cand_stride;
             __syncthreads();
-            for (int i = tid; i < cap2; i += kScanThreads) keys[i] = i < total ? __ldcg(&in[i]) : 0;
-            bitonic_sort_desc<kScanThreads>(keys, cap2);
-            const int n = min(total, a.k);
+            for (int i = tid; i < total; i += kScanThreads) keys[i] = __ldcg(&in[i]);
+            __syncthreads();
+            // k best of the survivors: histogram selection (a dozen barriers) instead of a full sort
+            uint64_t* sel_out = keys + kFusedSelectMax;
+            uint32_t* hist = reinterpret_cast<uint32_t*>(sel_out + kFusedSelOut);
+            const uint64_t* result = keys;
+            int n = -1;
+            if (total > 256 && a.k <= kFusedSelOut / 2) {
+                const int got = select_topk_smem<kScanThreads>(keys, total, a.k, hist, sel_out, kFusedSelOut);
+                if (got >= 0) {
+                    n = min(got, a.k);
+                    result = sel_out;
+                }
+            }
+            if (n < 0) {
+                for (int i = total + tid; i < cap2; i += kScanThreads) keys[i] = 0;
+                bitonic_sort_desc<kScanThreads>(keys, cap2);
+                n = min(total, a.k);
+            }
             int64_t* items = a.out_items + static_cast<size_t>(q) * a.k;
             float* scores = a.out_scores + static_cast<size_t>(q) * a.k;
             for (int j = tid; j < a.k; j += kScanThreads) {
                 int64_t item = -1;
                 float sc = 0.0f;
                 if (j < n) {
-                    const uint32_t kp = key_pos(keys[j]);
+                    const uint32_t kp = key_pos(result[j]);
                     const uint32_t pos = a.ties_low ? ~kp : kp;
                     if (kBlob && a.subset_in_params) item = blob.sub[pos];
                     else item = a.subset ? a.subset[pos] : static_cast<int64_t>(pos);
                     item += a.item_offset;
-                    sc = key_score(keys[j]);
+                    sc = key_score(result[j]);
                 }
                 items[j] = item;
                 scores[j] = sc;
@@ -393,8 +412,9 @@ cudaError_t launch_scan(const ScanArgs& a, cudaStream_t s) {
 }
 
 // ---- single-lookup latency form: query (and a short subset) in the kernel parameters ----------
-using SmallBlob = ParamBlob<kParamQuerySmall, 0>;
-using BigBlob = ParamBlob<kParamQueryBig, kParamSubsetMax>;
+using SmallBlob = ParamBlob<kParamQuerySmall, 0>;                   // 4 KB of parameters
+using MidBlob = ParamBlob<kParamQuerySmall, kParamSubsetSmall>;    // 8 KB
+using BigBlob = ParamBlob<kParamQueryBig, kParamSubsetMax>;        // 28 KB
 
 bool scan1_fits(int dim, int k, int64_t n_scan, int64_t subset_len, bool has_subset) {
     if (dim > kParamQueryBig) return false;
@@ -408,9 +428,9 @@ int scan1_grid(int device, int dim, int k, int64_t n_scan) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     int64_t tiles = (n_scan + kRoundRows - 1) / kRoundRows;
-    // small corpora: one CTA per SM (the last CTA's merge stays short); large ones: up to 4 per SM so that
-    // enough loads are in flight to fill HBM, as long as every CTA still has >= 8 rounds of rows
-    int64_t g = std::min<int64_t>(tiles, std::max<int64_t>(sms, std::min<int64_t>(tiles / 8, 4ll * sms)));
+    // up to 4 CTAs per SM (the general form's occupancy); the last CTA's merge cost does not grow with the
+    // number of survivors (histogram selection), only its buffer bounds the grid
+    int64_t g = std::min<int64_t>(tiles, 4ll * sms);    // one round of rows per CTA while the rows last
     g = std::min<int64_t>(g, kFusedSelectMax / std::max(k, 1));
     (void)dim;
     return static_cast<int>(std::max<int64_t>(g, 1));
@@ -426,18 +446,19 @@ static cudaError_t launch_scan1_t(const ScanArgs& a, const float* q_host, const 
     return launch_scan_t<T, 1>(a, blob, s);
 }
 
+template <typename T>
+static cudaError_t launch_scan1_d(const ScanArgs& a, const float* q_host, const int64_t* sub_host, cudaStream_t s) {
+    // the smallest parameter blob that holds the query (and the subset): the launch copies all of it
+    if (a.dim <= kParamQuerySmall && !sub_host) return launch_scan1_t<T, SmallBlob>(a, q_host, sub_host, s);
+    if (a.dim <= kParamQuerySmall && a.n_scan <= kParamSubsetSmall) return launch_scan1_t<T, MidBlob>(a, q_host, sub_host, s);
+    return launch_scan1_t<T, BigBlob>(a, q_host, sub_host, s);
+}
+
 cudaError_t launch_scan1(const ScanArgs& a, const float* q_host, const int64_t* sub_host, cudaStream_t s) {
-    const bool small = a.dim <= kParamQuerySmall && !sub_host;
     switch (a.dtype) {
-        case TAV_F32:
-            return small ? launch_scan1_t<float, SmallBlob>(a, q_host, sub_host, s)
-                         : launch_scan1_t<float, BigBlob>(a, q_host, sub_host, s);
-        case TAV_BF16:
-            return small ? launch_scan1_t<__nv_bfloat16, SmallBlob>(a, q_host, sub_host, s)
-                         : launch_scan1_t<__nv_bfloat16, BigBlob>(a, q_host, sub_host, s);
-        case TAV_F16:
-            return small ? launch_scan1_t<__half, SmallBlob>(a, q_host, sub_host, s)
-                         : launch_scan1_t<__half, BigBlob>(a, q_host, sub_host, s);
+        case TAV_F32: return launch_scan1_d<float>(a, q_host, sub_host, s);
+        case TAV_BF16: return launch_scan1_d<__nv_bfloat16>(a, q_host, sub_host, s);
+        case TAV_F16: return launch_scan1_d<__half>(a, q_host, sub_host, s);
     }
     return cudaErrorInvalidValue;
 }
