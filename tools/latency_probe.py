@@ -55,6 +55,13 @@ def main():
         t_numpy = bench(lambda: np.dot(v, q), n=300, warm=30)
         sub = np.random.default_rng(99).choice(rows, size=min(1000, rows), replace=False).tolist()
         t_subset = bench(lambda: base.fuzzy_lookup_embedding_in_subset(q, sub, 10, 0.0))
+        sub_np = np.asarray(sub, np.int64)
+        subp = sub_np.ctypes.data_as(C.c_void_p)
+
+        def raw_subset():
+            lib.tav_search(ix, qp, 1, 10, C.c_float(0.0), 0, subp, len(sub_np), 0, ip, sp, cp, None)
+
+        t_raw_subset = bench(raw_subset)
         t_aslist = bench(lambda: np.asarray(sub), n=300, warm=30)
         base.enable_timing()            # GPU-side duration of the one kernel (events add host time: separate pass)
         gpu_ms = []
@@ -65,7 +72,7 @@ def main():
         base.enable_timing(False)
         gpu_us = sorted(gpu_ms)[len(gpu_ms) // 2] * 1e3
         print(f"{rows}x{dim}: ctypes call {t_size:.1f} us | tav_search (raw ctypes) {t_raw:.1f} us | "
-              f"search_arrays {t_arrays:.1f} us | fuzzy_lookup_embedding {t_lookup:.1f} us | in_subset(1000) {t_subset:.1f} us "
+              f"search_arrays {t_arrays:.1f} us | fuzzy_lookup_embedding {t_lookup:.1f} us | in_subset(1000) {t_subset:.1f} us (raw ctypes {t_raw_subset:.1f} us) "
               f"(np.asarray(list) alone {t_aslist:.1f} us) | kernel on the GPU {gpu_us:.1f} us ({launches} "
               f"launch) | np.dot alone {t_numpy:.1f} us", flush=True)
 

@@ -81,7 +81,7 @@ constexpr int kMaxChunks = 512;                      // query chunks per launch 
 constexpr int kFinalizeFast = 8192;                 // finalize sorts up to this many candidates in one go
 constexpr int kMaxSegments = 320;                   // candidate segments per query (2 per unit of its chunk)
 // both forms: 192 KB of tiles + barriers + a small scratch used by the sampler's tail
-constexpr size_t kScratchBytes = static_cast<size_t>(kEpiWarps) * 32 * 33 * sizeof(float);  // admit_chunk rows (the sampler tail reuses it)
+constexpr size_t kScratchBytes = 2 * 128 * kSampleTop * sizeof(float);  // the sampler tail's exchange of partial top-8 lists
 constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(4) * kStageBytes + 256 + kScratchBytes;
 
 enum Mode { kSample = 0, kMain = 1, kDump = 2 };
@@ -120,48 +120,33 @@ __device__ __forceinline__ void insert_top(float (&top)[kSampleTop], float x) {
 }
 
 
-// Slow path of the MAIN epilogue, warp-cooperative.  Lane L holds 32 dots of ITS query (a chunk of the
-// tile's rows) and `hit` says whether one of them reaches its admission threshold.  Done lane by lane
-// (branch-free mask + 32 predicated stores, ~300 instructions, executed by the whole warp whenever ANY
-// lane hits) this was the bottleneck of small corpora: at 50k rows a warp hits in 93 % of its chunks.
-// Instead the hit lanes park their 32 values in shared memory (one conflict-free row each) and the warp
-// then walks the hit lanes together: lane j tests value j of lane L against L's threshold, the ballot
-// gives the admitted rows, and they are appended — coalesced — to L's private candidate segment.
-// Must be called convergently by the 32 lanes of a warp; rbase (a multiple of 32) and nvalid are
-// warp-uniform.
-constexpr int kAdmitRow = 33;  // floats per lane row (padded: conflict-free in both directions)
-__device__ __forceinline__ void admit_chunk(const uint32_t (&v)[32], bool hit, float tau, uint32_t rbase, int nvalid,
-                                            const uint32_t* row_mask, float* wscratch, uint64_t* my_cand,
-                                            uint32_t& n_admitted, uint32_t cap_seg, int lane) {
-    unsigned todo = __ballot_sync(0xFFFFFFFFu, hit);
-    if (todo == 0) return;
-    if (hit) {
+// MAIN epilogue of one 32-row chunk: this thread's 32 dots of ITS query against its admission threshold.
+// Two-level screen, all in registers: the maximum of each group of 8 dots (FMNMX3 trees) is tested first;
+// only a group that holds an admitted row runs the 8 predicated compare-and-store steps, appending
+// (dot, row) keys to the thread's PRIVATE candidate segment (one writer, a register counter).
+// Why this shape (profiles/README.md, "epilogue"): a shared per-query counter cost ~1 us of L2 round trip
+// per atomicAdd; a branch-free 32-bit mask + 32 predicated stores cost ~300 instructions whenever ANY of
+// the warp's 32 queries admitted a row (93 % of the chunks at 50k rows); a warp-cooperative walk over the
+// hit lanes was latency-bound on its shuffle / ballot / shared-memory chains (~2000 cycles per chunk).
+// `amask`: bit i set = row rbase + i exists and passes the row mask (warp-uniform).
+__device__ __forceinline__ void admit_chunk(const uint32_t (&v)[32], float tau, uint32_t rbase, uint32_t amask,
+                                            uint64_t* my_cand, uint32_t& n_admitted, uint32_t cap_seg) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) wscratch[lane * kAdmitRow + i] = __uint_as_float(v[i]);
-    }
-    __syncwarp();
-    uint32_t allowed = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
-    if (row_mask) allowed &= row_mask[rbase >> 5];
-    const bool lane_allowed = (allowed >> lane) & 1u;
-    const unsigned long long my_ptr = reinterpret_cast<unsigned long long>(my_cand);
-    while (todo) {
-        const int L = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const float x = wscratch[L * kAdmitRow + lane];
-        const float t = __shfl_sync(0xFFFFFFFFu, tau, L);
-        const bool ok = lane_allowed && x >= t;
-        const unsigned bits = __ballot_sync(0xFFFFFFFFu, ok);
-        if (bits) {
-            const uint32_t base = __shfl_sync(0xFFFFFFFFu, n_admitted, L);
-            uint64_t* dst = reinterpret_cast<uint64_t*>(__shfl_sync(0xFFFFFFFFu, my_ptr, L));
-            if (ok) {
-                const uint32_t slot = base + __popc(bits & ((1u << lane) - 1u));
-                if (slot < cap_seg) dst[slot] = (static_cast<uint64_t>(__float_as_uint(x)) << 32) | (rbase + lane);
+    for (int g = 0; g < 4; ++g) {
+        float m = fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]));
+#pragma unroll
+        for (int j = 2; j < 8; ++j) m = fmaxf(m, __uint_as_float(v[8 * g + j]));
+        if (m >= tau) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = 8 * g + j;
+                if (__uint_as_float(v[i]) >= tau && ((amask >> i) & 1u)) {
+                    if (n_admitted < cap_seg) my_cand[n_admitted] = (static_cast<uint64_t>(v[i]) << 32) | (rbase + i);
+                    ++n_admitted;
+                }
             }
-            if (lane == L) n_admitted += __popc(bits);
         }
     }
-    __syncwarp();
 }
 
 // Work distribution: unit u (a CTA, or a CTA pair) serves ONE query chunk, c = u % nqc, and every
@@ -369,7 +354,6 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int my_q = (unit % a.nqc) * kChunk + lane_q;
         uint64_t* const my_cand = a.cand + (static_cast<size_t>(my_q) * a.n_seg + seg) * a.cap_seg;
         uint32_t n_admitted = 0;
-        float* const wscratch = scratch + (warp - 2) * (32 * kAdmitRow);
         int t, c;
         for (int i = 0; get_item(a, unit, n_units, i, t, c); ++i) {
             const uint32_t item = static_cast<uint32_t>(i);
@@ -413,14 +397,10 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     }
                     return;
                 }
-                // MAIN.  Branch-free screen: the chunk's best dot; chunks that hold an admitted row take the
-                // warp-cooperative slow path (admit_chunk) into the thread's PRIVATE candidate segment — no
-                // atomics: with one shared counter per query the L2 round trip of its atomicAdd stalled the
-                // warp ~1 us per chunk (profiles/README.md).
-                float mx = __uint_as_float(v[0]);
-#pragma unroll
-                for (int i2 = 1; i2 < 32; ++i2) mx = fmaxf(mx, __uint_as_float(v[i2]));
-                admit_chunk(v, mx >= tau, tau, rbase, nvalid, a.row_mask, wscratch, my_cand, n_admitted, a.cap_seg, lane);
+                // MAIN: group-wise screen and private-segment append (admit_chunk)
+                uint32_t amask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+                if (a.row_mask) amask &= a.row_mask[rbase >> 5];
+                admit_chunk(v, tau, rbase, amask, my_cand, n_admitted, a.cap_seg);
             };
 
             uint32_t va[32], vb[32];
@@ -693,7 +673,6 @@ mma_ts_main_kernel(const __grid_constant__ CUtensorMap map_c, const TsArgs ta, c
         const int seg = (unit / a.nqc) * 2 + half;
         uint64_t* const my_cand = a.cand + (static_cast<size_t>(my_q) * a.n_seg + seg) * a.cap_seg;
         uint32_t n_admitted = 0;
-        float* const wscratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256) + (warp - 2) * (32 * kAdmitRow);
         const float tau = my_q < a.nq ? a.thr[my_q] : INFINITY;
         const int cols_warp = ta.tile_n / 2;  // 32 or 64 columns per epilogue warp
         int t, c;
@@ -709,10 +688,9 @@ mma_ts_main_kernel(const __grid_constant__ CUtensorMap map_c, const TsArgs ta, c
             auto process = [&](const uint32_t (&v)[32], int c0) {
                 const int nvalid = min(32, ncols - c0);
                 const uint32_t rbase = static_cast<uint32_t>(row0 + c0);  // a multiple of 32
-                float mx = __uint_as_float(v[0]);
-#pragma unroll
-                for (int i2 = 1; i2 < 32; ++i2) mx = fmaxf(mx, __uint_as_float(v[i2]));
-                admit_chunk(v, mx >= tau, tau, rbase, nvalid, a.row_mask, wscratch, my_cand, n_admitted, a.cap_seg, lane);
+                uint32_t amask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+                if (a.row_mask) amask &= a.row_mask[rbase >> 5];
+                admit_chunk(v, tau, rbase, amask, my_cand, n_admitted, a.cap_seg);
             };
             uint32_t va[32], vb[32];
             if (ncols > 0) ptx::tmem_ld_32x32(taddr, va);
@@ -1004,7 +982,8 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k, bool split, b
     p.n_main_tiles = static_cast<int>((n_rows + p.tile_n - 1) / p.tile_n);
     if (p.ts) {
         const size_t slab = static_cast<size_t>(p.tile_n / 2) * kBK * 2 * p.kb_count;
-        p.ts_stages = static_cast<int>(std::max<size_t>(2, std::min<size_t>(8, (200 * 1024) / slab)));
+        const size_t room = 232448 - 1024 - 256 - kScratchBytes;  // 227 KB per CTA minus alignment, barriers, scratch
+        p.ts_stages = static_cast<int>(std::max<size_t>(2, std::min<size_t>(8, room / slab)));
         p.ts_smem = 1024 + p.ts_stages * slab + 256 + kScratchBytes;
     }
     const int max_units = p.cg == 2 ? std::max(1, p.sms / 2) : p.sms;
@@ -1016,8 +995,11 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k, bool split, b
     // target = 16k — and never for k <= 8, because the 8 block maxima are 8 distinct admitted rows.
     // Overflow (> 8*target admitted) is rarer still.  Either way the query is merely redone by the exact
     // row scan.  Large corpora aim at 2048 rows, small ones at 128; never fewer than 16k.
-    const int64_t target = std::max<int64_t>(
-        16ll * k, std::min<int64_t>(2048, std::max<int64_t>(128, n_rows / 4096)));
+    // For k <= 8 nothing can starve, so small corpora aim much lower (32 rows: a quarter of the corpus is
+    // sampled, with the branch-free epilogue, and MAIN's epilogue then rarely has anything to append).
+    const int64_t target = k <= kSampleTop
+                               ? std::min<int64_t>(2048, std::max<int64_t>(32, n_rows / 4096))
+                               : std::max<int64_t>(16ll * k, std::min<int64_t>(2048, std::max<int64_t>(128, n_rows / 4096)));
     int64_t admitted = n_rows;  // rows a query is expected to admit
     if (n_rows <= 16384 || 8 * target >= n_rows || p.n_full_tiles < 8) {
         p.n_sample = 0;
