@@ -26,6 +26,7 @@ import typeagent_py_b200 as tab
 from oracle import ref_loader
 from oracle import vectorbase_oracle as O
 from tests.golden import cases as C
+from tests.parity import assert_hits_match
 
 needs_reference = pytest.mark.skipif(not ref_loader.reference_available(),
                                      reason="reference sources neither mounted nor vendored")
@@ -231,11 +232,10 @@ def test_embedding_file_pair_loads_into_a_search(tmp_path):
         for base, ref, k, ms in ((rel_base, ref_rel, 50, 0.85), (msg_base, ref_msg, 10, 0.7), (msg_base, ref_msg, 25, 0.0)):
             got = base.fuzzy_lookup_embedding(q, k, ms)
             want = ref.fuzzy_lookup_embedding(q, max_hits=k, min_score=ms)
-            assert [h.item for h in got] == [h.item for h in want]
-            np.testing.assert_allclose([h.score for h in got], [h.score for h in want], atol=1e-4, rtol=0)
+            assert_hits_match(got, want, min_score=ms, what="embedding file -> search")   # order up to float32 ties
     # SQLite BLOB layout (storage/sqlite/schema.py:193-212) through embeddings_from_blobs
     blobs = [row.tobytes() for row in messages]
     again = tab.VectorBase(settings)
     again.deserialize(formats.embeddings_from_blobs(blobs))
-    assert [h.item for h in again.fuzzy_lookup_embedding(epq[4], 10, 0.7)] == \
-           [h.item for h in ref_msg.fuzzy_lookup_embedding(epq[4], max_hits=10, min_score=0.7)]
+    assert_hits_match(again.fuzzy_lookup_embedding(epq[4], 10, 0.7),
+                      ref_msg.fuzzy_lookup_embedding(epq[4], max_hits=10, min_score=0.7), min_score=0.7)

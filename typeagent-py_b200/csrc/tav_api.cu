@@ -154,6 +154,7 @@ struct tav_index {
     int retry_cap = 0;
     std::vector<Pending> pending;
     int next_slot = 0;
+    int last_first_slot = -1, last_n_slots = 0;   // bookkeeping slots of the most recent search (-1: row scan)
     // float32 indexes: the rows as two fp16 planes for the tensor-core path (built lazily,
     // extended on append); split_flag[0] = a corpus value left the fp16 range
     DevBuf split_hi, split_lo, split_flag;
@@ -688,6 +689,13 @@ static int finish_pending(tav_index* ix, cudaStream_t s, int* redone) {
 
 extern "C" {
 
+const int32_t* tav_internal_retry_totals(tav_index* ix, int* count) {
+    if (count) *count = 0;
+    if (!ix || ix->last_first_slot < 0 || !ix->retry.p) return nullptr;
+    if (count) *count = ix->last_n_slots;
+    return retry_totals(ix, ix->last_first_slot);
+}
+
 int tav_finish_search(tav_index* ix, void* stream, int* redone) {
     if (!ix) return TAV_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ix->mu);
@@ -755,6 +763,8 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
     }
 
     const int64_t n_scan = subset ? subset_len : ix->size;
+    ix->last_first_slot = -1;
+    ix->last_n_slots = 0;
     TimedSearch* ts = cur_timed(ix);
     if (!ts) ts = &ix->untimed;
     const bool timing = ts != &ix->untimed;
@@ -957,6 +967,8 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
                 if (int rc = finish_pending(ix, s, &redone)) return rc;
             }
             const int slot = ix->next_slot++;
+            if (q0 == 0) ix->last_first_slot = slot;
+            ix->last_n_slots = slot - ix->last_first_slot + 1;
             MmaArgs m{};
             m.device = ix->device;
             m.corpus = use_split ? ix->split_hi.p : ix->rows;

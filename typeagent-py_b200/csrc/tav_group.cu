@@ -16,9 +16,9 @@
 //   arrive[world]  u32   arrive[r] = sequence number of the last search rank r PUBLISHED here
 //   ack[world]     u32   ack[r]    = sequence number of the last search rank r MERGED (it no longer
 //                                    reads what this rank published for it)
-//   redo[2][world] u32   finish protocol: (finish_seq << 8 | min(redone, 255)) + 1 per rank
-//   slots[depth][world][slot_bytes]   packed lists [items i64 | scores f32 | counts i32] (8-byte aligned
-//                                    sections, the layout ShardedVectorBase always used)
+//   slots[depth][world][slot_bytes]   packed lists [items i64 | scores f32 | counts i32 | tail] (8-byte
+//                                    aligned sections, the layout ShardedVectorBase always used; tail word
+//                                    0 = queries the rank's exact redo will still correct at finish)
 // `depth` searches may be in flight (deferred) before a rank has to wait for its peers' acks.
 
 #include <stdio.h>
@@ -62,9 +62,11 @@ __device__ __forceinline__ void spin_until(const uint32_t* p, uint32_t want) {
 // Publish: this rank's packed list (already in its own slot of its own region) -> the same slot in
 // every peer's region, then arrive[me] = seq everywhere.  Waits first until every peer acknowledged
 // the search that used this slot `depth` searches ago.
+// The last 16 bytes of a slot are its tail: word 0 = number of this rank's queries that its exact redo
+// will still correct at finish (read here from the local search's device counters).
 __global__ void __launch_bounds__(256)
 publish_kernel(PeerTable peers, int me, int world, size_t off_ack, size_t off_slot, size_t bytes, uint32_t seq,
-               uint32_t need_ack, uint32_t* ticket) {
+               uint32_t need_ack, uint32_t* ticket, const int32_t* retry_totals, int n_retry) {
     __shared__ int s_last;
     const char* src = peers.region[me] + off_slot;
     if (blockIdx.x == 0 && threadIdx.x < world && threadIdx.x != me) {
@@ -84,7 +86,13 @@ publish_kernel(PeerTable peers, int me, int world, size_t off_ack, size_t off_sl
         }
     }
     __syncthreads();
-    const size_t n16 = bytes / 16;  // slot sections are 8-byte aligned and padded to 16 by the host side
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+        uint32_t flagged = 0;
+        for (int i = 0; i < n_retry; ++i)  // flagged queries + "a query value left the fp16 range" (split form)
+            flagged += static_cast<uint32_t>(__ldcg(&retry_totals[2 * i])) + static_cast<uint32_t>(__ldcg(&retry_totals[2 * i + 1]));
+        *reinterpret_cast<uint32_t*>(peers.region[threadIdx.x] + off_slot + bytes - 16) = flagged;
+    }
+    const size_t n16 = (bytes - 16) / 16;  // sections are padded to 16 bytes by the host side; the tail goes separately
     for (int w = 0; w < world; ++w) {
         if (w == me) continue;
         uint4* dst = reinterpret_cast<uint4*>(peers.region[w] + off_slot);
@@ -110,40 +118,24 @@ publish_kernel(PeerTable peers, int me, int world, size_t off_ack, size_t off_sl
 
 // first kernel of a merge: wait for every rank's publish of `seq` (one tiny CTA; the merge kernel that
 // follows in stream order then reads complete lists)
-__global__ void wait_arrive_kernel(const uint32_t* arrive, int world, uint32_t seq) {
-    if (threadIdx.x < world) spin_until(arrive + threadIdx.x, seq);
+// ... and sum the ranks' "still to be corrected" counts (slot tails) into a mapped host word
+__global__ void wait_arrive_kernel(const uint32_t* arrive, int world, uint32_t seq, const char* slots, size_t slot_bytes,
+                                   size_t tail_off, uint32_t* flagged_host) {
+    __shared__ uint32_t s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncwarp();
+    if (threadIdx.x < world) {
+        spin_until(arrive + threadIdx.x, seq);
+        atomicAdd(&s_sum, *reinterpret_cast<const volatile uint32_t*>(slots + threadIdx.x * slot_bytes + tail_off));
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) *flagged_host = s_sum;
 }
 
 // last kernel of a merge: tell every peer that this rank is done reading the slots of `seq`
 __global__ void ack_kernel(PeerTable peers, int me, int world, size_t off_ack, uint32_t seq) {
     if (threadIdx.x < world && threadIdx.x != me)
         st_release_sys(reinterpret_cast<uint32_t*>(peers.region[threadIdx.x] + off_ack) + me, seq);
-}
-
-// finish protocol: publish this rank's count of exactly-redone queries, wait for everybody's, sum
-__global__ void redo_exchange_kernel(PeerTable peers, int me, int world, size_t off_redo, uint32_t fin_seq,
-                                     uint32_t redone, uint32_t* total_host) {
-    const uint32_t tag = ((fin_seq << 8) | min(redone, 255u)) + 1u;
-    const size_t off = off_redo + static_cast<size_t>(fin_seq & 1u) * world * sizeof(uint32_t);
-    __shared__ uint32_t s_sum;
-    if (threadIdx.x == 0) s_sum = 0;
-    __syncthreads();
-    if (threadIdx.x < world) {
-        st_release_sys(reinterpret_cast<uint32_t*>(peers.region[threadIdx.x] + off) + me, tag);
-        const uint32_t* mine = reinterpret_cast<const uint32_t*>(peers.region[me] + off) + threadIdx.x;
-        const long long t0 = clock64();
-        uint32_t v;
-        while ((((v = ld_acquire_sys(mine)) - 1u) >> 8) != (fin_seq & 0x00FFFFFFu) || v == 0) {
-            if (clock64() - t0 > kSpinLimit) __trap();
-            __nanosleep(64);
-        }
-        atomicAdd(&s_sum, (v - 1u) & 0xFFu);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        *total_host = s_sum;
-        __threadfence_system();
-    }
 }
 
 }  // namespace
@@ -155,13 +147,14 @@ using namespace tav;
 struct tav_group {
     int device = 0, rank = 0, world = 1, depth = 2;
     int max_queries = 0, max_k = 0;
-    size_t slot_bytes = 0, off_ack = 0, off_redo = 0, off_slots = 0, region_bytes = 0;
+    size_t slot_bytes = 0, off_ack = 0, off_slots = 0, region_bytes = 0;
     char* region = nullptr;           // this rank's exchange region (cudaMalloc)
     PeerTable peers{};                // region of every rank, as mapped here
     bool connected = false;
-    uint32_t seq = 0, fin_seq = 0;    // searches published / finishes exchanged so far
+    uint32_t seq = 0;                 // searches published so far
     uint32_t* ticket = nullptr;       // device counter of the publish kernel
-    uint32_t* total_host = nullptr;   // pinned: result of the redo exchange
+    uint32_t* flagged_host = nullptr; // pinned, mapped: [depth] world-wide "still to be corrected" counts per slot
+    std::vector<uint32_t> open_seqs;  // sequence numbers of the deferred searches since the last finish
     int64_t* merged_items = nullptr;  // where the last search's merged result went (for a re-merge at finish)
     float* merged_scores = nullptr;
     int32_t* merged_counts = nullptr;
@@ -177,7 +170,7 @@ static inline size_t a8(size_t v) { return (v + 7) & ~size_t(7); }
 static void packed_offsets(int nq, int k, size_t* off_scores, size_t* off_counts, size_t* total) {
     *off_scores = a8(static_cast<size_t>(nq) * k * 8);
     *off_counts = *off_scores + a8(static_cast<size_t>(nq) * k * 4);
-    *total = a16(*off_counts + a8(static_cast<size_t>(nq) * 4));
+    *total = a16(*off_counts + a8(static_cast<size_t>(nq) * 4)) + 16;  // + the tail
 }
 
 #define TAVG_CUDA(expr)                                                                            \
@@ -211,14 +204,14 @@ int tav_group_create(int device, int rank, int world, int max_queries, int max_k
     size_t os, oc;
     packed_offsets(max_queries, max_k, &os, &oc, &g->slot_bytes);
     g->off_ack = a16(static_cast<size_t>(world) * 4);
-    g->off_redo = g->off_ack + a16(static_cast<size_t>(world) * 4);
-    g->off_slots = (g->off_redo + a16(static_cast<size_t>(2) * world * 4) + 255) & ~size_t(255);
+    g->off_slots = (g->off_ack + a16(static_cast<size_t>(world) * 4) + 255) & ~size_t(255);
     g->region_bytes = g->off_slots + static_cast<size_t>(depth) * world * g->slot_bytes;
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&g->region), g->region_bytes);
     if (e == cudaSuccess) e = cudaMemset(g->region, 0, g->off_slots);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&g->ticket), 64);
     if (e == cudaSuccess) e = cudaMemset(g->ticket, 0, 64);
-    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&g->total_host), 64);
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&g->flagged_host), 64 * sizeof(uint32_t));
+    if (e == cudaSuccess) memset(g->flagged_host, 0, 64 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         set_error("tav_group_create: %s", cudaGetErrorString(e));
@@ -263,7 +256,7 @@ int tav_group_destroy(tav_group* g) {
         if (r != g->rank && g->peers.region[r]) cudaIpcCloseMemHandle(g->peers.region[r]);
     if (g->region) cudaFree(g->region);
     if (g->ticket) cudaFree(g->ticket);
-    if (g->total_host) cudaFreeHost(g->total_host);
+    if (g->flagged_host) cudaFreeHost(g->flagged_host);
     delete g;
     return TAV_OK;
 }
@@ -277,8 +270,8 @@ int tav_group_capacity(const tav_group* g, int* max_queries, int* max_k, int* de
 }
 
 // exchange + merge of the list this rank holds in its own slot for sequence number `seq`
-static int publish_and_merge(tav_group* g, int nq, int k, uint32_t seq, int64_t* out_items, float* out_scores,
-                             int32_t* out_counts, cudaStream_t s) {
+static int publish_and_merge(tav_group* g, int nq, int k, uint32_t seq, const int32_t* retry_totals, int n_retry,
+                             int64_t* out_items, float* out_scores, int32_t* out_counts, cudaStream_t s) {
     const int slot = static_cast<int>(seq % static_cast<uint32_t>(g->depth));
     size_t off_scores, off_counts, bytes;
     packed_offsets(nq, k, &off_scores, &off_counts, &bytes);
@@ -289,9 +282,11 @@ static int publish_and_merge(tav_group* g, int nq, int k, uint32_t seq, int64_t*
         const uint32_t need_ack = seq - static_cast<uint32_t>(g->depth);
         const uint32_t need = seq > static_cast<uint32_t>(g->depth) ? need_ack : 0u;
         publish_kernel<<<grid, 256, 0, s>>>(g->peers, g->rank, g->world, g->off_ack, off_mine, bytes, seq, need,
-                                            g->ticket);
+                                            g->ticket, retry_totals, retry_totals ? n_retry : 0);
         TAVG_CUDA(cudaGetLastError());
-        wait_arrive_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const uint32_t*>(g->region), g->world, seq);
+        wait_arrive_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const uint32_t*>(g->region), g->world, seq,
+                                            g->region + g->off_slots + static_cast<size_t>(slot) * g->world * g->slot_bytes,
+                                            g->slot_bytes, bytes - 16, g->flagged_host + slot);
         TAVG_CUDA(cudaGetLastError());
     }
     // lists of all ranks for this slot lie side by side in MY region: strides between ranks = slot_bytes
@@ -348,8 +343,11 @@ int tav_sharded_search(tav_index* ix, tav_group* g, const float* queries_device,
                             reinterpret_cast<int32_t*>(mine + off_counts), stream);
         if (rc != TAV_OK) return rc;
     }
-    int rc = publish_and_merge(g, n_queries, k, seq, out_items, out_scores, out_counts, s);
+    int n_retry = 0;
+    const int32_t* retry_totals = tav_size(ix) == 0 ? nullptr : tav_internal_retry_totals(ix, &n_retry);
+    int rc = publish_and_merge(g, n_queries, k, seq, retry_totals, n_retry, out_items, out_scores, out_counts, s);
     if (rc != TAV_OK) return rc;
+    g->open_seqs.push_back(seq);
     g->merged_items = out_items;
     g->merged_scores = out_scores;
     g->merged_counts = out_counts;
@@ -371,18 +369,18 @@ int tav_sharded_finish(tav_index* ix, tav_group* g, void* stream, int* redone_to
     TAVG_CUDA(cudaSetDevice(g->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int redone = 0;
-    int rc = tav_finish_search(ix, stream, &redone);  // synchronises; corrects this rank's slot(s) in place
+    int rc = tav_finish_search(ix, stream, &redone);  // corrects this rank's slot(s) in place
     if (rc != TAV_OK) return rc;
+    // Every rank summed the same slot tails in its wait kernel: the world-wide number of queries that some
+    // rank has just corrected.  One stream synchronise (tav_finish_search already did it when anything
+    // was pending on this rank) makes the mapped words current; no second exchange.
+    TAVG_CUDA(cudaStreamSynchronize(s));
     uint32_t total = static_cast<uint32_t>(redone);
     if (g->world > 1) {
-        const uint32_t fin = ++g->fin_seq;
-        *g->total_host = 0;
-        redo_exchange_kernel<<<1, 32, 0, s>>>(g->peers, g->rank, g->world, g->off_redo, fin,
-                                              static_cast<uint32_t>(redone), g->total_host);
-        TAVG_CUDA(cudaGetLastError());
-        TAVG_CUDA(cudaStreamSynchronize(s));
-        total = *g->total_host;
+        total = 0;
+        for (uint32_t sq : g->open_seqs) total += g->flagged_host[sq % static_cast<uint32_t>(g->depth)];
     }
+    g->open_seqs.clear();
     const int outstanding = g->outstanding;
     g->outstanding = 0;
     if (total > 0) {
@@ -399,7 +397,8 @@ int tav_sharded_finish(tav_index* ix, tav_group* g, void* stream, int* redone_to
             char* to = g->region + g->off_slots + (static_cast<size_t>(new_slot) * g->world + g->rank) * g->slot_bytes;
             TAVG_CUDA(cudaMemcpyAsync(to, from, bytes, cudaMemcpyDeviceToDevice, s));
         }
-        rc = publish_and_merge(g, g->last_nq, g->last_k, seq, g->merged_items, g->merged_scores, g->merged_counts, s);
+        rc = publish_and_merge(g, g->last_nq, g->last_k, seq, nullptr, 0, g->merged_items, g->merged_scores,
+                               g->merged_counts, s);
         if (rc != TAV_OK) return rc;
         TAVG_CUDA(cudaStreamSynchronize(s));
         if (outstanding > 1) {

@@ -132,3 +132,14 @@ cudaError_t launch_mma_dump(const MmaArgs& a, void* workspace, size_t workspace_
 void set_error(const char* fmt, ...);
 
 }  // namespace tav
+
+// library-internal (not in include/tavec.h): device address of the "queries flagged for the exact redo"
+// counters of the index's most recent search — `*count` int32 words, 2 words apart — or nullptr when that
+// search ran on the row-scan path (nothing to flag).  The sharded search ships their sum with the
+// published candidate list so that every rank learns, without a second exchange, whether some rank will
+// correct its candidates at finish.
+extern "C" const int32_t* tav_internal_retry_totals(tav_index* ix, int* count);
+
+namespace tav {
+
+}  // namespace tav

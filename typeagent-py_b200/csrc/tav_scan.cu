@@ -314,7 +314,14 @@ scan_rows_kernel(const ScanArgs a, const __grid_constant__ BLOB blob) {
             while (cap2 < total) cap2 <<= 1;
             const uint64_t* in = a.cand_keys + static_cast<size_t>(q) * a.cand_stride;
             __syncthreads();
-            for (int i = tid; i < total; i += kScanThreads) keys[i] = __ldcg(&in[i]);
+            for (int i0 = tid; i0 < total; i0 += 4 * kScanThreads) {  // four independent loads in flight per thread
+                uint64_t e[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e[u] = i0 + u * kScanThreads < total ? __ldcg(&in[i0 + u * kScanThreads]) : 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + u * kScanThreads < total) keys[i0 + u * kScanThreads] = e[u];
+            }
             __syncthreads();
             // k best of the survivors: histogram selection (a dozen barriers) instead of a full sort
             uint64_t* sel_out = keys + kFusedSelectMax;
