@@ -151,6 +151,7 @@ struct tav_index {
     // "redo exactly" bookkeeping of the tensor-core path, one slot per outstanding search:
     // [kMaxPending][2] int32 {flagged queries, a query value left the fp16 range} | [kMaxPending][retry_cap] flags
     DevBuf retry;
+    PinBuf retry_host;  // mapped pinned twin of the [kMaxPending][2] totals: tav_finish_search reads it without a D2H copy
     int retry_cap = 0;
     std::vector<Pending> pending;
     int next_slot = 0;
@@ -283,6 +284,7 @@ int tav_destroy(tav_index* ix) {
         b->release();
     ix->pin_in.release();
     ix->pin_out.release();
+    ix->retry_host.release();
     for (auto& b : ix->pin_append) b.release();
     if (ix->ev_pin_in) cudaEventDestroy(ix->ev_pin_in);
     for (auto& ev : ix->ev_append)
@@ -649,12 +651,12 @@ static int finish_pending(tav_index* ix, cudaStream_t s, int* redone) {
     if (ix->pending.empty()) return TAV_OK;
     int32_t totals[2 * kMaxPending];
     int corpus_overflow = 0;
-    TAV_CUDA(cudaMemcpyAsync(totals, ix->retry.p, sizeof(totals), cudaMemcpyDeviceToHost, s));
     bool any_split = false;
     for (const Pending& p : ix->pending) any_split |= p.split;
     if (any_split)
         TAV_CUDA(cudaMemcpyAsync(&corpus_overflow, ix->split_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     TAV_CUDA(cudaStreamSynchronize(s));
+    memcpy(totals, ix->retry_host.p, sizeof(totals));  // written by the kernels through the mapping; current after the sync
     std::vector<Pending> todo;
     todo.swap(ix->pending);
     ix->next_slot = 0;
@@ -682,7 +684,11 @@ static int finish_pending(tav_index* ix, cudaStream_t s, int* redone) {
             if (rc != TAV_OK) return rc;
         }
     }
-    if (dirty) TAV_CUDA(cudaMemsetAsync(ix->retry.p, 0, sizeof(totals), s));
+    if (dirty) {
+        TAV_CUDA(cudaMemsetAsync(ix->retry.p, 0, sizeof(totals), s));
+        TAV_CUDA(cudaStreamSynchronize(s));
+        memset(ix->retry_host.p, 0, sizeof(totals));
+    }
     if (redone) *redone = n_redone;
     return TAV_OK;
 }
@@ -914,8 +920,13 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
             ts->launches += 1;
         } else {
             const void* src = queries;
-            if (q_bytes <= kPinnedStageLimit) {
-                // via pinned staging: a pageable source would make the copy synchronous
+            cudaPointerAttributes qa{};
+            const bool q_pinned = !o_dev &&  // (device outputs: the call returns before the copy ends, staging protects the caller's buffer)
+                                  cudaPointerGetAttributes(&qa, queries) == cudaSuccess && qa.type == cudaMemoryTypeHost;
+            if (!q_pinned) cudaGetLastError();
+            if (q_bytes <= kPinnedStageLimit && !q_pinned) {
+                // via pinned staging: a pageable source would make the copy synchronous (a caller that
+                // already passes pinned memory is copied from directly)
                 const size_t sub_bytes = subset ? static_cast<size_t>(subset_len) * sizeof(int64_t) : 0;
                 const size_t sub_off = sub_bytes <= kPinnedStageLimit ? ((sub_bytes + 15) & ~size_t(15)) : 0;
                 TAV_CUDA(pin_in_acquire(ix, sub_off + q_bytes));
@@ -952,6 +963,8 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
             const size_t bytes = (static_cast<size_t>(2) * kMaxPending + static_cast<size_t>(kMaxPending) * cap) * sizeof(int32_t);
             TAV_CUDA(ix->retry.ensure(bytes));
             TAV_CUDA(cudaMemsetAsync(ix->retry.p, 0, 2 * kMaxPending * sizeof(int32_t), s));
+            TAV_CUDA(ix->retry_host.ensure(2 * kMaxPending * sizeof(int32_t)));
+            memset(ix->retry_host.p, 0, 2 * kMaxPending * sizeof(int32_t));
             ix->retry_cap = cap;
         }
         if (timing)  // the events of this search exist before the launcher records them
@@ -988,6 +1001,8 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
             m.out_counts = d_counts + q0;
             m.retry_flags = retry_flags(ix, slot);
             m.retry_total = retry_totals(ix, slot);
+            m.retry_total_host = static_cast<int32_t*>(ix->retry_host.p) + 2 * slot;
+            m.split_overflow_host = use_split ? static_cast<int*>(ix->retry_host.p) + 2 * slot + 1 : nullptr;
             m.row_mask = d_mask;
             m.no_ts = (flags & TAV_NO_TMEM_QUERIES) ? 1 : 0;
             int ev_used = 0;

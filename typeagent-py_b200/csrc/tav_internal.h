@@ -114,6 +114,8 @@ struct MmaArgs {
     int32_t* out_counts;
     int32_t* retry_flags;  // device [nq]: set to 1 for queries the caller must redo with the row scan
     int32_t* retry_total;  // device [1]: incremented once per flagged query (never reset by the kernels)
+    int32_t* retry_total_host;  // the same counter in mapped pinned memory (read by the host without a copy), or nullptr
+    int* split_overflow_host;   // split only: mapped pinned twin of split_overflow, or nullptr
     const uint32_t* row_mask;  // optional device bitmask over corpus rows (bit set = row may be returned)
     int no_ts;             // 1: never use the Q-stationary (queries in tensor memory) form
     cudaEvent_t (*ev)[2];  // optional event pairs, one recorded around every kernel launched

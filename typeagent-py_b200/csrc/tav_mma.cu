@@ -748,8 +748,8 @@ __global__ void query_prep_kernel(const float* q, T* out, int nq, int nq_pad, in
 // Rows >= n_valid are zero-filled (query padding).  |x| must be below the fp16 range; a value
 // that is not sets *overflow and the caller redoes the search with the exact row scan.
 __global__ void split_rows_kernel(const float* src, __half* hi, __half* lo, int64_t n_valid, int64_t n_total,
-                                  int dim, int* overflow, int init_state, float floor_score, float* thr,
-                                  float* floor_out, int32_t* retry) {
+                                  int dim, int* overflow, int* overflow_host, int init_state, float floor_score,
+                                  float* thr, float* floor_out, int32_t* retry) {
     const int64_t total = n_total * dim;
     const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     bool bad = false;
@@ -761,7 +761,10 @@ __global__ void split_rows_kernel(const float* src, __half* hi, __half* lo, int6
         lo[i] = __float2half_rn(rest);
         bad |= fabsf(x) > 60000.0f;
     }
-    if (bad) atomicOr(overflow, 1);
+    if (bad) {
+        atomicOr(overflow, 1);
+        if (overflow_host) atomicOr(overflow_host, 1);
+    }
     if (init_state && tid < n_valid)
         init_query_state(static_cast<int>(tid), static_cast<int>(n_valid), floor_score, thr, floor_out, retry);
 }
@@ -773,7 +776,8 @@ constexpr int kSelOut = 1024;
 __global__ void __launch_bounds__(kSelectThreads)
 finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, int n_seg, uint32_t cap_seg, int fast_cap,
                 const float* thr, const float* floor_x, int k, int64_t item_offset, int64_t* out_items,
-                float* out_scores, int32_t* out_counts, int32_t* retry, int32_t* retry_total) {
+                float* out_scores, int32_t* out_counts, int32_t* retry, int32_t* retry_total,
+                int32_t* retry_total_host) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* sel_out = keys + fast_cap;
@@ -821,6 +825,7 @@ finalize_kernel(const uint64_t* cand, const uint32_t* cand_count, int n_seg, uin
             out_counts[q] = 0;
             retry[q] = 1;
             atomicAdd(retry_total, 1);
+            if (retry_total_host) atomicAdd(retry_total_host, 1);  // mapped pinned copy: the host reads it without a D2H
         }
         return;
     }
@@ -1098,8 +1103,8 @@ cudaError_t prep_queries(const MmaArgs& a, void* dst, void* dst_lo, int nq_pad, 
         std::min<int64_t>((total + 255) / 256, 148 * 8), init_state ? (a.nq + 255) / 256 : 1));
     if (a.split) {
         split_rows_kernel<<<grid, 256, 0, s>>>(a.queries, static_cast<__half*>(dst), static_cast<__half*>(dst_lo),
-                                               a.nq, nq_pad, a.dim, a.split_overflow, init_state, a.floor_score, thr,
-                                               floor_out, a.retry_flags);
+                                               a.nq, nq_pad, a.dim, a.split_overflow, a.split_overflow_host, init_state,
+                                               a.floor_score, thr, floor_out, a.retry_flags);
         return cudaGetLastError();
     }
     if (a.dtype == TAV_BF16)
@@ -1125,7 +1130,7 @@ cudaError_t launch_split_rows(const float* src, void* hi, void* lo, int64_t n, i
     const int64_t total = n * dim;
     const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));
     split_rows_kernel<<<grid, 256, 0, s>>>(src, static_cast<__half*>(hi), static_cast<__half*>(lo), n, n, dim, overflow,
-                                           0, 0.0f, nullptr, nullptr, nullptr);
+                                           nullptr, 0, 0.0f, nullptr, nullptr, nullptr);
     return cudaGetLastError();
 }
 
@@ -1308,7 +1313,7 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
     if ((e = ev_begin()) != cudaSuccess) return e;
     finalize_kernel<<<a.nq, kSelectThreads, sel_smem, s>>>(d_cand, d_count, p.n_seg, p.cap_seg, fast_cap, d_thr, d_floor,
                                                            a.k, a.item_offset, a.out_items, a.out_scores,
-                                                           a.out_counts, a.retry_flags, a.retry_total);
+                                                           a.out_counts, a.retry_flags, a.retry_total, a.retry_total_host);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = ev_end(2)) != cudaSuccess) return e;
     ++n_launch;
