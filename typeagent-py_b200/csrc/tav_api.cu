@@ -9,7 +9,9 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <mutex>
@@ -854,6 +856,18 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
         a.done_seq = ++ix->done_seq;
         if (a.done_seq == 0) a.done_seq = ++ix->done_seq;
         *done = 0;
+        static const bool trace_on = getenv("TAV_TRACE") != nullptr;
+        unsigned long long* trace_host = nullptr;
+        unsigned long long t_host0 = 0;
+        if (trace_on) {  // diagnostic: phase stamps of the kernel in mapped pinned memory, printed to stderr
+            TAV_CUDA(ix->pin_in.ensure(4096));
+            trace_host = reinterpret_cast<unsigned long long*>(static_cast<char*>(ix->pin_in.p) + 2048);
+            memset(trace_host, 0, 64);
+            a.trace = trace_host;
+            timespec tsn;
+            clock_gettime(CLOCK_MONOTONIC, &tsn);
+            t_host0 = static_cast<unsigned long long>(tsn.tv_sec) * 1000000000ull + tsn.tv_nsec;
+        }
         if (timing) {
             TAV_CUDA(ev_record(ts->total[0], s));
             TAV_CUDA(ev_record(ts->ev[0][0], s));
@@ -879,6 +893,20 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
             if ((spin & 0x3FFF) == 0x3FFF && cudaStreamQuery(s) != cudaErrorNotReady) break;
         }
         if (!seen) TAV_CUDA(cudaStreamSynchronize(s));
+        if (trace_host) {
+            timespec tsn;
+            clock_gettime(CLOCK_MONOTONIC, &tsn);
+            const unsigned long long t_host1 = static_cast<unsigned long long>(tsn.tv_sec) * 1000000000ull + tsn.tv_nsec;
+            cudaStreamSynchronize(s);
+            static int printed = 0;
+            if (++printed % 500 == 0)
+                fprintf(stderr, "[tav trace] grid %d: staged +%.1f us, scanned +%.1f, handed +%.1f, merge starts +%.1f, hits "
+                                "written +%.1f, flag +%.1f (kernel %.1f us) | host call until flag seen %.1f us\n", a.grid,
+                        (trace_host[1] - trace_host[0]) / 1e3, (trace_host[2] - trace_host[1]) / 1e3,
+                        (trace_host[3] - trace_host[2]) / 1e3, (trace_host[4] - trace_host[0]) / 1e3,
+                        (trace_host[5] - trace_host[4]) / 1e3, (trace_host[6] - trace_host[5]) / 1e3,
+                        (trace_host[6] - trace_host[0]) / 1e3, (t_host1 - t_host0) / 1e3);
+        }
         const char* h = static_cast<const char*>(ix->pin_out.p);
         memcpy(out_items, h, nk * sizeof(int64_t));
         memcpy(out_scores, h + off_scores, nk * sizeof(float));

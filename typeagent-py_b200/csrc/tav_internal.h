@@ -37,6 +37,7 @@ struct ScanArgs {
     int32_t* out_counts;
     uint32_t* done_flag;      // mapped pinned host word set to done_seq once the hits are written, or nullptr
     uint32_t done_seq;
+    unsigned long long* trace;  // diagnostic (TAV_TRACE=1): %globaltimer stamps of the single-launch form's phases
 };
 constexpr int kFusedSelectMax = 8192;   // survivors the last CTA of the single-launch form can merge
 constexpr int kFusedSelOut = 1024;      // ... of which it sorts at most this many after the histogram selection

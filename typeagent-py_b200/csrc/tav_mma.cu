@@ -1023,7 +1023,8 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k, bool split, b
     {
         // every unit of a chunk owns two candidate segments per query (one per epilogue column half):
         // room for 16x the expected share of a segment, and for every row it can see when nothing is cut
-        const int per_chunk = std::max(1, std::min(std::max(1, max_units / p.nqc), p.n_main_tiles));
+        const int per_chunk =
+            std::max(1, std::min(std::min(std::max(1, max_units / p.nqc), p.n_main_tiles), kMaxSegments / 2));
         p.main_units = per_chunk * p.nqc;
         p.n_seg = 2 * per_chunk;
         const int64_t tiles_per_unit = (p.n_main_tiles + per_chunk - 1) / per_chunk;

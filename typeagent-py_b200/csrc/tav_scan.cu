@@ -134,10 +134,21 @@ struct BlobTraits<NoBlob> {
     static constexpr bool kHas = false;
 };
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TAV_STAMP(slot)                                                   \
+    do {                                                                  \
+        if (a.trace && threadIdx.x == 0) a.trace[(slot)] = global_ns();   \
+    } while (0)
+
 template <typename T, int QB, bool VEC, typename BLOB>
 __global__ void __launch_bounds__(kScanThreads)
 scan_rows_kernel(const ScanArgs a, const __grid_constant__ BLOB blob) {
     constexpr bool kBlob = BlobTraits<BLOB>::kHas;
+    if (blockIdx.x == 0) TAV_STAMP(0);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NV = kRowsPerWarp * QB;
     const int dim = a.dim;
@@ -164,6 +175,10 @@ scan_rows_kernel(const ScanArgs a, const __grid_constant__ BLOB blob) {
     if (tid < QB) {
         s_cnt[tid] = 0;
         s_admit[tid] = floor_key;
+    }
+    if (blockIdx.x == 0) {
+        __syncthreads();
+        TAV_STAMP(1);  // query staged
     }
 
     const T* corpus = reinterpret_cast<const T*>(a.corpus);
@@ -280,6 +295,7 @@ scan_rows_kernel(const ScanArgs a, const __grid_constant__ BLOB blob) {
 
     // hand the CTA's best k per query to the global candidate buffers
     __syncthreads();
+    if (blockIdx.x == 0) TAV_STAMP(2);  // rows scanned
 #pragma unroll
     for (int q = 0; q < QB; ++q) {
         if (q >= a.nq) break;
@@ -305,7 +321,9 @@ scan_rows_kernel(const ScanArgs a, const __grid_constant__ BLOB blob) {
             if (s_is_last) *a.fused_ticket = 0;  // ready for the next search
         }
         __syncthreads();
+        if (blockIdx.x == 0) TAV_STAMP(3);  // survivors handed over
         if (!s_is_last) return;
+        TAV_STAMP(4);  // last CTA starts the merge
         __threadfence();
         uint64_t* keys = skeys;  // the lists are dead now; room for kFusedSelectMax keys was reserved
         for (int q = 0; q < a.nq; ++q) {
@@ -361,6 +379,7 @@ scan_rows_kernel(const ScanArgs a, const __grid_constant__ BLOB blob) {
                 a.cand_count[q] = 0;
             }
         }
+        TAV_STAMP(5);  // hits written
         if (a.done_flag) {
             // ONE system-scope fence, by the thread that raises the completion word: the barrier orders the
             // other threads' result stores before it (a membar.sys per thread cost ~20 us here: each waits
@@ -371,6 +390,7 @@ scan_rows_kernel(const ScanArgs a, const __grid_constant__ BLOB blob) {
                 *reinterpret_cast<volatile uint32_t*>(a.done_flag) = a.done_seq;
             }
         }
+        TAV_STAMP(6);  // completion word raised
     }
 }
 
