@@ -480,8 +480,14 @@ def measure(bn: Bench, name, w, steps, warmup, *, force=None, sustain_s=0.0, par
         # timed region; they are counted and reported
         fallbacks[0] += base.finish_search() if sharded is None else sharded.finish()
 
+    q_one = q_host.numpy()[0]
+
     def step_e2e():
         # public host API: pinned host queries -> H2D -> search -> D2H of the hits
+        if sharded is None and batch == 1:
+            # the reference's own call shape (tools/benchmark_vectorbase.py:97-109): one embedding in,
+            # list[ScoredInt] out
+            return base.fuzzy_lookup_embedding(q_one, max_hits=k, min_score=w["min_score"])
         if sharded is None:
             return base.search_arrays(q_host.numpy(), k, w["min_score"],
                                       out=(out_items.numpy(), out_scores.numpy(), out_counts.numpy()))
@@ -562,6 +568,7 @@ def measure(bn: Bench, name, w, steps, warmup, *, force=None, sustain_s=0.0, par
         wall_e2e += time.perf_counter() - t0
         ms_e2e_local += e0.elapsed_time(e1)
     ms_e2e = bn.max_over_ranks(ms_e2e_local)
+    lt_e2e = base.last_timing()                 # the last e2e step's device-side share (first launch -> last result byte)
     clocks = sampler.summary() if sampler else None
 
     # sustained: >= sustain_s seconds of back-to-back steps (the power cap engages after ~50 ms)
@@ -621,7 +628,9 @@ def measure(bn: Bench, name, w, steps, warmup, *, force=None, sustain_s=0.0, par
         "e2e": {"value": batch / (e2e_ms_step / 1e3), "unit": "queries/s",
                 "h2d_bytes_per_step": batch * dim * 4, "d2h_bytes_per_step": batch * k * 12 + batch * 4,
                 "ms_per_step": e2e_ms_step, "wall_ms_per_step": wall_e2e * 1e3 / steps,
-                "api": "VectorBase.search_arrays(host float32 queries) -> host int64/float32 hits"},
+                "device_search_ms_last_step": lt_e2e["total_ms"], "main_kernel_ms_last_step": lt_e2e["scan_ms"],
+                "api": ("VectorBase.fuzzy_lookup_embedding(host float32 embedding) -> list[ScoredInt]" if batch == 1 and world == 1
+                        else "VectorBase.search_arrays(host float32 queries) -> host int64/float32 hits")},
         "gpu_launches": launches_per_step * steps,
         "exact_fallback_queries": fallbacks[0],
         "parity_checked": parity_checked, "parity": parity_note,

@@ -200,6 +200,38 @@ __device__ int select_topk_smem(const uint64_t* keys, int total, int k, uint32_t
     return n;
 }
 
+// ---- system-scope flags between GPUs (csrc/tav_group.cu: peer-memory candidate exchange) -------------
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr long long kSpinLimit = 8000000000ll;  // ~4 s of clock64: a lost peer traps instead of hanging the box
+// returns once *p has reached `want` (sequence numbers wrap: compared as a signed distance)
+__device__ __forceinline__ void spin_until(const uint32_t* p, uint32_t want) {
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(ld_acquire_sys(p) - want) < 0) {
+        if (clock64() - t0 > kSpinLimit) __trap();
+        __nanosleep(64);
+    }
+}
+
+// What a merge of a sharded search waits for and signals (all device pointers; arrive == nullptr: plain merge)
+struct MergeSync {
+    const uint32_t* arrive;    // [world] sequence number of the last list every rank published into THIS rank's region
+    int world;
+    uint32_t seq;              // the search being merged
+    uint32_t* ack[16];         // ack[w]: this rank's acknowledgement word in rank w's region
+    int me;
+    uint32_t* ticket;          // device counter (zero on entry, self-resetting): last-CTA-done
+    const char* tails;         // slot tails of the world's lists: tails + r * slot_bytes, word 0 = "still to be corrected"
+    size_t slot_bytes;
+    uint32_t* flagged_host;    // mapped pinned word receiving the world-wide sum of the tails
+};
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs a driver call; remember, per device, the
 // largest size already granted to a kernel and only call again to raise it.
 template <typename Kernel>

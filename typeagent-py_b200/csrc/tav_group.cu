@@ -36,28 +36,10 @@ namespace tav {
 namespace {
 
 constexpr int kMaxWorld = 16;
-constexpr long long kSpinLimit = 8000000000ll;  // ~4 s of clock64: a lost peer traps instead of hanging the box
 
 struct PeerTable {
     char* region[kMaxWorld];  // region[r] = base of rank r's exchange region as mapped in THIS process
 };
-
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// true once *p has reached `want` (sequence numbers wrap: compare as a signed distance)
-__device__ __forceinline__ void spin_until(const uint32_t* p, uint32_t want) {
-    const long long t0 = clock64();
-    while (static_cast<int32_t>(ld_acquire_sys(p) - want) < 0) {
-        if (clock64() - t0 > kSpinLimit) __trap();
-        __nanosleep(64);
-    }
-}
 
 // Publish: this rank's packed list (already in its own slot of its own region) -> the same slot in
 // every peer's region, then arrive[me] = seq everywhere.  Waits first until every peer acknowledged
@@ -114,28 +96,6 @@ publish_kernel(PeerTable peers, int me, int world, size_t off_ack, size_t off_sl
             st_release_sys(reinterpret_cast<uint32_t*>(peers.region[threadIdx.x]) + me, seq);  // arrive[me] at rank w
         if (threadIdx.x == 0) *ticket = 0;
     }
-}
-
-// first kernel of a merge: wait for every rank's publish of `seq` (one tiny CTA; the merge kernel that
-// follows in stream order then reads complete lists)
-// ... and sum the ranks' "still to be corrected" counts (slot tails) into a mapped host word
-__global__ void wait_arrive_kernel(const uint32_t* arrive, int world, uint32_t seq, const char* slots, size_t slot_bytes,
-                                   size_t tail_off, uint32_t* flagged_host) {
-    __shared__ uint32_t s_sum;
-    if (threadIdx.x == 0) s_sum = 0;
-    __syncwarp();
-    if (threadIdx.x < world) {
-        spin_until(arrive + threadIdx.x, seq);
-        atomicAdd(&s_sum, *reinterpret_cast<const volatile uint32_t*>(slots + threadIdx.x * slot_bytes + tail_off));
-    }
-    __syncwarp();
-    if (threadIdx.x == 0) *flagged_host = s_sum;
-}
-
-// last kernel of a merge: tell every peer that this rank is done reading the slots of `seq`
-__global__ void ack_kernel(PeerTable peers, int me, int world, size_t off_ack, uint32_t seq) {
-    if (threadIdx.x < world && threadIdx.x != me)
-        st_release_sys(reinterpret_cast<uint32_t*>(peers.region[threadIdx.x] + off_ack) + me, seq);
 }
 
 }  // namespace
@@ -277,29 +237,38 @@ static int publish_and_merge(tav_group* g, int nq, int k, uint32_t seq, const in
     packed_offsets(nq, k, &off_scores, &off_counts, &bytes);
     const size_t off_mine = g->off_slots + (static_cast<size_t>(slot) * g->world + g->rank) * g->slot_bytes;
     if (g->world > 1) {
-        const int grid = static_cast<int>(std::min<size_t>(32, std::max<size_t>(1, bytes / (16 * 256 * 4))));
+        // enough CTAs to keep the NVLink stores in flight (2.1 MB at B = 256, k = 100 over 8 ranks): one per 2 KB
+        const int grid = static_cast<int>(std::min<size_t>(128, std::max<size_t>(1, bytes / 2048)));
         // the slot was last used by search seq - depth: every peer must have merged that one
         const uint32_t need_ack = seq - static_cast<uint32_t>(g->depth);
         const uint32_t need = seq > static_cast<uint32_t>(g->depth) ? need_ack : 0u;
         publish_kernel<<<grid, 256, 0, s>>>(g->peers, g->rank, g->world, g->off_ack, off_mine, bytes, seq, need,
                                             g->ticket, retry_totals, retry_totals ? n_retry : 0);
         TAVG_CUDA(cudaGetLastError());
-        wait_arrive_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const uint32_t*>(g->region), g->world, seq,
-                                            g->region + g->off_slots + static_cast<size_t>(slot) * g->world * g->slot_bytes,
-                                            g->slot_bytes, bytes - 16, g->flagged_host + slot);
-        TAVG_CUDA(cudaGetLastError());
     }
-    // lists of all ranks for this slot lie side by side in MY region: strides between ranks = slot_bytes
+    // lists of all ranks for this slot lie side by side in MY region: strides between ranks = slot_bytes.
+    // The merge itself waits for every rank's publish (acquire spin on the arrive words), and its last CTA
+    // acknowledges to the peers and sums the slot tails: no separate wait / ack launches.
     const char* base = g->region + g->off_slots + static_cast<size_t>(slot) * g->world * g->slot_bytes;
+    MergeSync sync{};
+    if (g->world > 1) {
+        sync.arrive = reinterpret_cast<const uint32_t*>(g->region);
+        sync.world = g->world;
+        sync.seq = seq;
+        for (int w = 0; w < g->world; ++w)
+            sync.ack[w] = reinterpret_cast<uint32_t*>(g->peers.region[w] + g->off_ack) + g->rank;
+        sync.me = g->rank;
+        sync.ticket = g->ticket + 8;
+        sync.tails = base + bytes - 16;
+        sync.slot_bytes = g->slot_bytes;
+        sync.flagged_host = g->flagged_host + slot;
+    }
     TAVG_CUDA(launch_merge(g->world, nq, k, reinterpret_cast<const int64_t*>(base),
                            reinterpret_cast<const float*>(base + off_scores),
                            reinterpret_cast<const int32_t*>(base + off_counts),
                            static_cast<int64_t>(g->slot_bytes / 8), static_cast<int64_t>(g->slot_bytes / 4),
-                           static_cast<int64_t>(g->slot_bytes / 4), out_items, out_scores, out_counts, s));
-    if (g->world > 1) {
-        ack_kernel<<<1, 32, 0, s>>>(g->peers, g->rank, g->world, g->off_ack, seq);
-        TAVG_CUDA(cudaGetLastError());
-    }
+                           static_cast<int64_t>(g->slot_bytes / 4), out_items, out_scores, out_counts, s,
+                           g->world > 1 ? &sync : nullptr));
     return TAV_OK;
 }
 

@@ -8,6 +8,8 @@
 
 namespace tav {
 
+struct MergeSync;  // tav_common.cuh
+
 // ---- row-scan path (tav_scan.cu) -------------------------------------------------------
 struct ScanArgs {
     const void* corpus;       // [n_corpus, dim] storage dtype, row-major dense
@@ -82,7 +84,7 @@ cudaError_t launch_fold_groups(int n_queries, int k, const int32_t* row_to_group
 cudaError_t launch_merge(int n_lists, int n_queries, int k, const int64_t* items,
                          const float* scores, const int32_t* counts, int64_t items_stride,
                          int64_t scores_stride, int64_t counts_stride, int64_t* out_items,
-                         float* out_scores, int32_t* out_counts, cudaStream_t s);
+                         float* out_scores, int32_t* out_counts, cudaStream_t s, const MergeSync* sync = nullptr);
 
 // rows [n, dim] of src dtype -> dst dtype (RNE), optionally L2-normalised per row (fp32 math)
 cudaError_t launch_convert(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,

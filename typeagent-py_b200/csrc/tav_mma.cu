@@ -98,7 +98,10 @@ struct KernelArgs {
     int n_seg;             // MAIN: candidate segments per query = 2 * (units per chunk)
     float* thr;            // [nq_pad] admission threshold (raw dot) per query: SAMPLE writes, MAIN reads
     float* floor_x;        // SAMPLE: [nq_pad] the caller's min_score as a dot floor
-    float* sample_max;     // SAMPLE: [n_tiles_work * 2, nq_pad] block maxima
+    float* sample_max;     // SAMPLE: [n_tiles_work * 2 * sample_gph, nq_pad] block maxima
+    int sample_gph;        // SAMPLE: blocks per thread per tile: 1 (128 rows each), 4 (32 rows) or 16 (8 rows)
+    int sample_use;        // SAMPLE: blocks the threshold is derived from ...
+    int sample_stride;     //         ... every sample_stride-th of the stored ones
     uint32_t* sample_done; // SAMPLE: [nqc * CG] finished-unit counters (self-resetting)
     int32_t* retry;        // SAMPLE: [nq] per-query "redo exactly" flags, cleared here
     float floor_score;     // SAMPLE: (float)min_score
@@ -385,15 +388,30 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     return;
                 }
                 if (MODE == kSample) {
-                    // branch-free: sample tiles are full tiles, every column is a real row
-                    if (a.row_mask) {
-                        const uint32_t bits = a.row_mask[rbase >> 5];
+                    // branch-free: sample tiles are full tiles, every column is a real row.  Maxima of the
+                    // four groups of 8 rows, then — by the block size the planner chose — stored per group
+                    // (blocks of 8 rows), per chunk (32) or folded into the tile maximum (128).
+                    const uint32_t bits = a.row_mask ? a.row_mask[rbase >> 5] : 0xFFFFFFFFu;
+                    float g4[4];
 #pragma unroll
-                        for (int i2 = 0; i2 < 32; ++i2)
-                            if ((bits >> i2) & 1u) bmax = fmaxf(bmax, __uint_as_float(v[i2]));
+                    for (int g = 0; g < 4; ++g) {
+                        float m = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int i2 = 8 * g + j;
+                            m = fmaxf(m, ((bits >> i2) & 1u) ? __uint_as_float(v[i2]) : -INFINITY);
+                        }
+                        g4[g] = m;
+                    }
+                    const float cm = fmaxf(fmaxf(g4[0], g4[1]), fmaxf(g4[2], g4[3]));
+                    float* dst = a.sample_max + (static_cast<size_t>(t) * 2 + half) * a.sample_gph * a.nq_pad + q;
+                    if (a.sample_gph == 16) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) dst[static_cast<size_t>((c0 >> 3) + g) * a.nq_pad] = g4[g];
+                    } else if (a.sample_gph == 4) {
+                        dst[static_cast<size_t>(c0 >> 5) * a.nq_pad] = cm;
                     } else {
-#pragma unroll
-                        for (int i2 = 0; i2 < 32; ++i2) bmax = fmaxf(bmax, __uint_as_float(v[i2]));
+                        bmax = fmaxf(bmax, cm);
                     }
                     return;
                 }
@@ -438,7 +456,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 if (CG == 2) ptx::mbar_arrive_cluster(lead_tempty0 + as * 8);
                 else ptx::mbar_arrive(&tempty[as]);
             }
-            if (MODE == kSample)
+            if (MODE == kSample && a.sample_gph == 1)
                 a.sample_max[(static_cast<size_t>(t) * 2 + half) * a.nq_pad + q] = bmax;
         }
         if (MODE == kSample) __threadfence();  // block maxima visible device-wide before the unit signs off
@@ -478,7 +496,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             const int te = threadIdx.x - 64;          // 0..255
             const int ql = te & (kBM - 1), part = te >> 7;
             const int q = c * kChunk + static_cast<int>(cta_rank) * kBM + ql;
-            const int n_blocks = a.n_tiles_work * 2;
+            const int n_blocks = a.sample_use;  // blocks j * sample_stride of the stored ones, j < sample_use
             float top[kSampleTop];
 #pragma unroll
             for (int i = 0; i < kSampleTop; ++i) top[i] = -INFINITY;
@@ -488,7 +506,8 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int b = b0 + 2 * u;
-                    x[u] = b < n_blocks ? __ldcg(&a.sample_max[static_cast<size_t>(b) * a.nq_pad + q]) : -INFINITY;
+                    x[u] = b < n_blocks ? __ldcg(&a.sample_max[static_cast<size_t>(b) * a.sample_stride * a.nq_pad + q])
+                                        : -INFINITY;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) insert_top(top, x[u]);
@@ -951,6 +970,9 @@ struct Plan {
     int n_full_tiles;
     int kb_count;
     int n_sample;      // tiles in the sample pass (0 = no sampling)
+    int sample_gph;    // blocks per thread per tile in the sample pass (block = 128 / sample_gph rows)
+    int sample_use;    // blocks the threshold uses, every sample_stride-th of the stored ones
+    int sample_stride;
     int sample_units;  // a multiple of nqc
     int main_units;    // a multiple of nqc
     int n_seg;         // candidate segments per query = 2 * main_units / nqc
@@ -1009,10 +1031,20 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k, bool split, b
     if (n_rows <= 16384 || 8 * target >= n_rows || p.n_full_tiles < 8) {
         p.n_sample = 0;
     } else {
+        // Block size: the m-th largest of L block maxima sits at the row quantile p when 1 - (1-p)^b = m / L;
+        // for p * b well above 1 every block clears the quantile and the maxima say nothing about it (the
+        // threshold would come out too high and queries starve).  So mid-size corpora — where the target is a
+        // larger fraction of the rows — use blocks of 32 or 8 rows instead of a thread's 128.
         const double prob = static_cast<double>(target) / static_cast<double>(n_rows);
-        const double q_b = 1.0 - pow(1.0 - prob, 128.0);
+        const int block_rows = prob * 128 <= 0.7 ? 128 : (prob * 32 <= 0.7 ? 32 : 8);
+        p.sample_gph = 128 / block_rows;
+        const double q_b = 1.0 - pow(1.0 - prob, static_cast<double>(block_rows));
         const int64_t blocks = static_cast<int64_t>(ceil(kSampleTop / q_b));
-        p.n_sample = static_cast<int>(std::min<int64_t>(p.n_full_tiles, std::max<int64_t>(4, (blocks + 1) / 2)));
+        const int64_t per_tile = 2ll * p.sample_gph;
+        p.n_sample = static_cast<int>(std::min<int64_t>(p.n_full_tiles, std::max<int64_t>(4, (blocks + per_tile - 1) / per_tile)));
+        const int64_t stored = static_cast<int64_t>(p.n_sample) * per_tile;
+        p.sample_use = static_cast<int>(std::min<int64_t>(blocks, stored));
+        p.sample_stride = static_cast<int>(std::max<int64_t>(1, stored / p.sample_use));
         admitted = target;
     }
     // sample units: chunk-bound (unit u serves chunk u % nqc), so a multiple of nqc
@@ -1043,7 +1075,7 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k, bool split, b
     p.off_q_lo = off;  // lo plane of the queries (split form only; reserved always)
     off = align(off + static_cast<size_t>(p.nq_pad) * dim * 2);
     p.off_sample = off;  // block maxima [n_sample * 2, nq_pad]
-    off = align(off + static_cast<size_t>(std::max(1, p.n_sample)) * 2 * p.nq_pad * sizeof(float));
+    off = align(off + static_cast<size_t>(std::max(1, p.n_sample)) * 2 * std::max(1, p.sample_gph) * p.nq_pad * sizeof(float));
     p.off_thr = off;
     off = align(off + static_cast<size_t>(p.nq_pad) * sizeof(float));
     p.off_floor = off;
@@ -1243,6 +1275,9 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
     ka.thr = d_thr;
     ka.floor_x = d_floor;
     ka.sample_max = d_sample;
+    ka.sample_gph = std::max(1, p.sample_gph);
+    ka.sample_use = p.sample_use;
+    ka.sample_stride = std::max(1, p.sample_stride);
     ka.sample_done = d_done;
     ka.retry = a.retry_flags;
     ka.floor_score = a.floor_score;

@@ -120,7 +120,7 @@ struct NoBlob {
     int32_t sub[1];
 };
 template <int QN, int SN>
-struct ParamBlob {
+struct alignas(16) ParamBlob {
     float q[QN];
     int32_t sub[SN > 0 ? SN : 1];
 };
@@ -165,7 +165,10 @@ scan_rows_kernel(const ScanArgs a, const __grid_constant__ BLOB blob) {
 
     // stage the queries (zero-fill unused slots)
     if constexpr (kBlob) {
-        for (int i = tid; i < dim; i += kScanThreads) sq[i] = blob.q[i];
+        // 16-byte constant-bank loads (LDC.128): a divergent-index LDC is serialised per lane
+        const float4* bq = reinterpret_cast<const float4*>(blob.q);
+        float4* sq4 = reinterpret_cast<float4*>(sq);
+        for (int i = tid; i < (dim + 3) / 4; i += kScanThreads) sq4[i] = bq[i];
     } else {
         for (int i = tid; i < QB * dim; i += kScanThreads) {
             const int q = i / dim;
@@ -558,12 +561,16 @@ cudaError_t launch_select(const SelectArgs& a, cudaStream_t s) {
 __global__ void __launch_bounds__(kSelectThreads)
 merge_kernel(int n_lists, int n_queries, int k, const int64_t* items, const float* scores,
              const int32_t* counts, int64_t items_stride, int64_t scores_stride,
-             int64_t counts_stride, int64_t* out_items, float* out_scores, int32_t* out_counts) {
+             int64_t counts_stride, int64_t* out_items, float* out_scores, int32_t* out_counts, const MergeSync sync) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
     __shared__ int s_cnt;
     __shared__ uint64_t s_admit;
     const int q = blockIdx.x, tid = threadIdx.x;
+    if (sync.arrive) {  // sharded search: every rank's list for this search must have landed in this rank's region
+        if (tid < sync.world) spin_until(sync.arrive + tid, sync.seq);
+        __syncthreads();
+    }
     const int cap = 1 << (32 - __clz(k + kSelectThreads - 1));
     if (tid == 0) {
         s_cnt = 0;
@@ -606,12 +613,35 @@ merge_kernel(int n_lists, int n_queries, int k, const int64_t* items, const floa
         out_scores[static_cast<size_t>(q) * k + j] = sc;
     }
     if (tid == 0) out_counts[q] = n;
+    if (sync.arrive) {
+        // last CTA done: nobody on this rank reads the slots of `seq` any more -> acknowledge to every peer
+        // (their next publish into this slot waits for it) and add up the "still to be corrected" tails
+        __shared__ int s_last_cta;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t t = atomicAdd(sync.ticket, 1u);
+            s_last_cta = t == gridDim.x - 1;
+            if (s_last_cta) *sync.ticket = 0;
+        }
+        __syncthreads();
+        if (s_last_cta) {
+            __threadfence();
+            if (tid < sync.world && tid != sync.me) st_release_sys(sync.ack[tid], sync.seq);
+            if (tid == 0) {
+                uint32_t sum = 0;
+                for (int r = 0; r < sync.world; ++r)
+                    sum += *reinterpret_cast<const volatile uint32_t*>(sync.tails + static_cast<size_t>(r) * sync.slot_bytes);
+                *sync.flagged_host = sum;
+            }
+        }
+    }
 }
 
 cudaError_t launch_merge(int n_lists, int n_queries, int k, const int64_t* items,
                          const float* scores, const int32_t* counts, int64_t items_stride,
                          int64_t scores_stride, int64_t counts_stride, int64_t* out_items,
-                         float* out_scores, int32_t* out_counts, cudaStream_t s) {
+                         float* out_scores, int32_t* out_counts, cudaStream_t s, const MergeSync* sync) {
     if (items_stride == 0) items_stride = static_cast<int64_t>(n_queries) * k;
     if (scores_stride == 0) scores_stride = static_cast<int64_t>(n_queries) * k;
     if (counts_stride == 0) counts_stride = n_queries;
@@ -619,10 +649,11 @@ cudaError_t launch_merge(int n_lists, int n_queries, int k, const int64_t* items
     static int granted[16] = {};
     cudaError_t e = ensure_dynamic_smem(merge_kernel, smem, granted);
     if (e != cudaSuccess) return e;
+    MergeSync none{};
     merge_kernel<<<n_queries, kSelectThreads, smem, s>>>(n_lists, n_queries, k, items, scores,
                                                          counts, items_stride, scores_stride,
                                                          counts_stride, out_items, out_scores,
-                                                         out_counts);
+                                                         out_counts, sync ? *sync : none);
     return cudaGetLastError();
 }
 
