@@ -838,7 +838,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
         a.floor_score = min_score;
         a.k = k;
         a.grid = scan1_grid(ix->device, ix->dim, k, n_scan);
-        a.cand_stride = a.grid * k;
+        a.cand_stride = a.grid * std::max(k, 32);   // a CTA hands over up to one round of 32 rows unsorted
         TAV_CUDA(ix->cand_keys.ensure(static_cast<size_t>(a.cand_stride) * sizeof(uint64_t)));
         a.cand_keys = static_cast<uint64_t*>(ix->cand_keys.p);
         a.cand_count = d_count;

@@ -196,7 +196,31 @@ __device__ int select_topk_smem(const uint64_t* keys, int total, int k, uint32_t
     int cap = 32;
     while (cap < n) cap <<= 1;
     for (int i = n + tid; i < cap; i += THREADS) out[i] = 0;
-    bitonic_sort_desc<THREADS>(out, cap);
+    if (cap <= 64) {
+        // a handful of survivors: one warp sorts them with warp-level barriers only (a CTA barrier per
+        // bitonic pass costs more than the pass)
+        __syncthreads();
+        if (tid < 32) {
+            for (int size = 2; size <= cap; size <<= 1) {
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    __syncwarp();
+                    for (int t = tid; t < (cap >> 1); t += 32) {
+                        const int lo2 = 2 * t - (t & (stride - 1));
+                        const int hi2 = lo2 + stride;
+                        const bool desc = (lo2 & size) == 0;
+                        const uint64_t x = out[lo2], y = out[hi2];
+                        if ((x < y) == desc) {
+                            out[lo2] = y;
+                            out[hi2] = x;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    } else {
+        bitonic_sort_desc<THREADS>(out, cap);
+    }
     return n;
 }
 
