@@ -549,6 +549,18 @@ def measure(bn: Bench, name, w, steps, warmup, *, force=None, sustain_s=0.0, par
     sampler = ClockSampler(bn.local_rank) if rank == 0 else None
     ms_resident = bn.max_over_ranks(timed_resident(steps))
     hist = history(steps)                       # the SAME pass as ms_resident
+    # rank-to-rank spread of the local search (a sharded step ends when the SLOWEST rank has published)
+    per_rank = None
+    if world > 1:
+        mine = (statistics.fmean(hist["main"]) if hist["main"] else None,
+                statistics.fmean(hist["search_total"]) if hist["search_total"] else None)
+        gathered = [None] * world
+        bn.dist.all_gather_object(gathered, mine)
+        mains = [g[0] for g in gathered if g and g[0] is not None]
+        totals = [g[1] for g in gathered if g and g[1] is not None]
+        if mains and totals:
+            per_rank = {"main_kernel_ms": {"min": min(mains), "max": max(mains)},
+                        "local_search_ms": {"min": min(totals), "max": max(totals)}}
     lt = base.last_timing()
     launches_per_step = lt["launches"] + (2 if world > 1 else 0)
     path = lt["path"]
@@ -649,6 +661,11 @@ def measure(bn: Bench, name, w, steps, warmup, *, force=None, sustain_s=0.0, par
         },
         "clocks": clocks,
     }
+    if per_rank:
+        per_rank["exchange_and_skew_ms"] = ms_step - per_rank["local_search_ms"]["max"]
+        per_rank["note"] = ("a sharded step = the slowest rank's local search + candidate exchange (publish over NVLink, "
+                            "flag wait, merge); exchange_and_skew = ms_per_step - the slowest rank's local search")
+        out["per_rank"] = per_rank
     if peaks.get("bf16_tflops") and path in ("mma", "mma_split"):
         rf = out["roofline"]
         rf["tensor_tflops"] = flops / (kernel_ms / 1e3) / 1e12
@@ -715,7 +732,7 @@ def run_b200(args, w):
                           parity=not args.no_parity, cpu=not args.no_cpu_baseline, cpu_queries=args.cpu_queries)
             if res is not None:
                 keep = ("metric", "value", "unit", "ms_per_step", "path", "e2e", "roofline", "cpu_baseline",
-                        "parity_checked", "exact_fallback_queries", "gpu_launches", "config")
+                        "parity_checked", "exact_fallback_queries", "gpu_launches", "config", "per_rank")
                 secondary[name] = {kk: res[kk] for kk in keep if kk in res}
     if out is not None:
         if secondary:

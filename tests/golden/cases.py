@@ -79,7 +79,9 @@ CASES: list[dict] = [
                   ("lookup", dict(max_hits=10, min_score=0.99)),
                   ("subset", dict(subset=("choice", 99, 10000, 1000), max_hits=10, min_score=0.0)),
                   ("subset", dict(subset=("choice", 7, 10000, 37), max_hits=50, min_score=0.5)),
-                  ("predicate", dict(predicate="mod3", max_hits=10, min_score=0.5))]),
+                  ("predicate", dict(predicate="mod3", max_hits=10, min_score=0.5)),
+                  # max_hits=0 on the predicate path slices [:0]: nothing (the argpartition path returns everything)
+                  ("predicate", dict(predicate="mod3", max_hits=0, min_score=0.5))]),
     dict(name="tiny_k_exceeds_n", make=("synthetic", dict(n=7, d=5, seed=5)),
          lookups=[("lookup", dict(max_hits=10, min_score=0.0)),
                   ("lookup", dict(max_hits=3, min_score=0.0)),

@@ -83,17 +83,20 @@ publish_kernel(PeerTable peers, int me, int world, size_t off_ack, size_t off_sl
              i += static_cast<size_t>(gridDim.x) * blockDim.x)
             dst[i] = s4[i];
     }
-    __threadfence_system();
+    // ONE system-scope fence per CTA, by the thread that takes the ticket: the barrier orders the CTA's peer
+    // stores before it (a membar.sys in each of the 32k threads was most of this kernel's time)
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const uint32_t t = atomicAdd(ticket, 1u) & 0x7FFFFFFFu;
         s_last = t == gridDim.x - 1;
     }
     __syncthreads();
     if (s_last) {
-        __threadfence_system();
-        if (threadIdx.x < world)
+        if (threadIdx.x < world) {
+            __threadfence_system();
             st_release_sys(reinterpret_cast<uint32_t*>(peers.region[threadIdx.x]) + me, seq);  // arrive[me] at rank w
+        }
         if (threadIdx.x == 0) *ticket = 0;
     }
 }
