@@ -88,6 +88,38 @@ __device__ __forceinline__ void list_compact(CandList l, int cap, int k, uint64_
     __syncthreads();
 }
 
+// The k largest of n <= 128 keys in shared memory, k <= 32, by ONE warp: every lane holds up to four keys
+// in registers and the warp extracts the maximum k times (shuffle reduction; keys are unique).  No CTA
+// barriers — list_compact's bitonic sort of 128 slots costs 28 of them (~3 us) for the same job.
+// Called by warp 0 only; keys[0..k) receive the result in descending order, returns min(n, k).
+__device__ __forceinline__ int warp_topk_small(uint64_t* keys, int n, int k) {
+    const int lane = threadIdx.x & 31;
+    uint64_t r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[j] = lane + 32 * j < n ? keys[lane + 32 * j] : 0;
+    __syncwarp();
+    const int out = min(n, k);
+    for (int i = 0; i < out; ++i) {
+        uint64_t m = r[0] > r[1] ? r[0] : r[1];
+        const uint64_t m2 = r[2] > r[3] ? r[2] : r[3];
+        m = m > m2 ? m : m2;
+        uint64_t w = m;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, w, off);
+            w = o > w ? o : w;
+        }
+        if (m == w && w != 0) {  // the owner retires it (unique keys: exactly one lane, one register)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (r[j] == w) r[j] = 0;
+        }
+        if (lane == 0) keys[i] = w;
+    }
+    __syncwarp();
+    return out;
+}
+
 // returns 1 when the list is now above `watermark` (compaction needed before the next round)
 __device__ __forceinline__ int list_push(CandList l, uint64_t key, int watermark) {
     const int slot = atomicAdd(l.count, 1);

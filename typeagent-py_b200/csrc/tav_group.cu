@@ -117,6 +117,13 @@ struct tav_group {
     uint32_t seq = 0;                 // searches published so far
     uint32_t* ticket = nullptr;       // device counter of the publish kernel
     uint32_t* flagged_host = nullptr; // pinned, mapped: [depth] world-wide "still to be corrected" counts per slot
+    // Deferred searches run their exchange (publish + merge) on the group's own stream, behind an event that
+    // follows the local search: the next search's kernels start at once on the caller's stream and the wait
+    // for the slowest rank no longer sits between two searches.  tav_sharded_finish joins the streams.
+    cudaStream_t xstream = nullptr;
+    cudaEvent_t ev_local[64] = {};    // [depth] local search of the slot's search done (caller's stream)
+    cudaEvent_t ev_merged[64] = {};   // [depth] merged result complete (exchange stream)
+    bool x_pending = false;           // something was enqueued on xstream since the last join
     std::vector<uint32_t> open_seqs;  // sequence numbers of the deferred searches since the last finish
     int64_t* merged_items = nullptr;  // where the last search's merged result went (for a re-merge at finish)
     float* merged_scores = nullptr;
@@ -173,6 +180,11 @@ int tav_group_create(int device, int rank, int world, int max_queries, int max_k
     if (e == cudaSuccess) e = cudaMemset(g->region, 0, g->off_slots);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&g->ticket), 64);
     if (e == cudaSuccess) e = cudaMemset(g->ticket, 0, 64);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->xstream, cudaStreamNonBlocking);
+    for (int i = 0; e == cudaSuccess && i < depth; ++i) {
+        e = cudaEventCreateWithFlags(&g->ev_local[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_merged[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&g->flagged_host), 64 * sizeof(uint32_t));
     if (e == cudaSuccess) memset(g->flagged_host, 0, 64 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -220,6 +232,11 @@ int tav_group_destroy(tav_group* g) {
     if (g->region) cudaFree(g->region);
     if (g->ticket) cudaFree(g->ticket);
     if (g->flagged_host) cudaFreeHost(g->flagged_host);
+    for (int i = 0; i < 64; ++i) {
+        if (g->ev_local[i]) cudaEventDestroy(g->ev_local[i]);
+        if (g->ev_merged[i]) cudaEventDestroy(g->ev_merged[i]);
+    }
+    if (g->xstream) cudaStreamDestroy(g->xstream);
     delete g;
     return TAV_OK;
 }
@@ -317,8 +334,20 @@ int tav_sharded_search(tav_index* ix, tav_group* g, const float* queries_device,
     }
     int n_retry = 0;
     const int32_t* retry_totals = tav_size(ix) == 0 ? nullptr : tav_internal_retry_totals(ix, &n_retry);
-    int rc = publish_and_merge(g, n_queries, k, seq, retry_totals, n_retry, out_items, out_scores, out_counts, s);
+    // deferred (pipelined) searches: exchange on the group's stream, ordered after the local search by an event
+    cudaStream_t xs = s;
+    if (defer && g->world > 1) {
+        TAVG_CUDA(cudaEventRecord(g->ev_local[slot], s));
+        TAVG_CUDA(cudaStreamWaitEvent(g->xstream, g->ev_local[slot], 0));
+        xs = g->xstream;
+    } else if (g->x_pending) {  // a synchronous search after deferred ones: their exchanges come first
+        TAVG_CUDA(cudaEventRecord(g->ev_merged[slot], g->xstream));
+        TAVG_CUDA(cudaStreamWaitEvent(s, g->ev_merged[slot], 0));
+        g->x_pending = false;
+    }
+    int rc = publish_and_merge(g, n_queries, k, seq, retry_totals, n_retry, out_items, out_scores, out_counts, xs);
     if (rc != TAV_OK) return rc;
+    if (xs != s) g->x_pending = true;
     g->open_seqs.push_back(seq);
     g->merged_items = out_items;
     g->merged_scores = out_scores;
@@ -340,6 +369,12 @@ int tav_sharded_finish(tav_index* ix, tav_group* g, void* stream, int* redone_to
     if (g->outstanding == 0) return TAV_OK;
     TAVG_CUDA(cudaSetDevice(g->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (g->x_pending) {  // join: the merged results of the deferred searches are complete on the caller's stream
+        const int slot = static_cast<int>(g->seq % static_cast<uint32_t>(g->depth));
+        TAVG_CUDA(cudaEventRecord(g->ev_merged[slot], g->xstream));
+        TAVG_CUDA(cudaStreamWaitEvent(s, g->ev_merged[slot], 0));
+        g->x_pending = false;
+    }
     int redone = 0;
     int rc = tav_finish_search(ix, stream, &redone);  // corrects this rank's slot(s) in place
     if (rc != TAV_OK) return rc;

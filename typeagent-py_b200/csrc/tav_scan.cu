@@ -303,9 +303,21 @@ scan_rows_kernel(const ScanArgs a, const __grid_constant__ BLOB blob) {
     for (int q = 0; q < QB; ++q) {
         if (q >= a.nq) break;
         CandList l{skeys + static_cast<size_t>(q) * cap, &s_cnt[q], &s_admit[q]};
-        // two-kernel form: hand over the CTA's best k.  Single-launch form: up to one round's worth of keys go
-        // over unsorted (the last CTA selects anyway; sorting 128 slots here cost ~3 us of barriers per CTA)
-        if (s_cnt[q] > (a.fused ? max(a.k, kRoundRows) : a.k)) list_compact<kScanThreads>(l, cap, a.k, floor_key);
+        // Hand over the CTA's best k.  Single-launch form on a small grid: up to one round's worth of keys
+        // goes over unsorted (the last CTA selects anyway).  Otherwise the k best are extracted — by one warp
+        // with shuffles when the list is short and k small (no CTA barriers), else by the bitonic compaction.
+        const int keep_all = (a.fused && static_cast<int64_t>(gridDim.x) * kRoundRows <= 2048) ? max(a.k, kRoundRows) : a.k;
+        if (s_cnt[q] > keep_all) {  // CTA-uniform
+            if (a.k <= 32 && s_cnt[q] <= 128) {
+                if (warp == 0) {
+                    const int kept = warp_topk_small(l.keys, s_cnt[q], a.k);
+                    if (lane == 0) s_cnt[q] = kept;
+                }
+                __syncthreads();
+            } else {
+                list_compact<kScanThreads>(l, cap, a.k, floor_key);
+            }
+        }
         const int n = s_cnt[q];
         if (tid == 0 && n > 0) s_base[q] = atomicAdd(&a.cand_count[q], static_cast<uint32_t>(n));
         __syncthreads();
@@ -455,7 +467,7 @@ bool scan1_fits(int dim, int k, int64_t n_scan, int64_t subset_len, bool has_sub
     if (has_subset && subset_len > kParamSubsetMax) return false;
     // the last CTA sorts every CTA's k survivors at once: a full wave of CTAs must fit its buffer
     const int64_t tiles = (n_scan + kRoundRows - 1) / kRoundRows;
-    return static_cast<int64_t>(std::max(k, kRoundRows)) * std::min<int64_t>(tiles, 148) <= kFusedSelectMax;
+    return static_cast<int64_t>(k) * std::min<int64_t>(tiles, 148) <= kFusedSelectMax;
 }
 
 int scan1_grid(int device, int dim, int k, int64_t n_scan) {
@@ -465,7 +477,7 @@ int scan1_grid(int device, int dim, int k, int64_t n_scan) {
     // up to 4 CTAs per SM (the general form's occupancy); the last CTA's merge cost does not grow with the
     // number of survivors (histogram selection), only its buffer bounds the grid
     int64_t g = std::min<int64_t>(tiles, 4ll * sms);    // one round of rows per CTA while the rows last
-    g = std::min<int64_t>(g, kFusedSelectMax / std::max(k, kRoundRows));  // a CTA hands over up to max(k, 32) keys
+    g = std::min<int64_t>(g, kFusedSelectMax / std::max(k, 1));
     (void)dim;
     return static_cast<int>(std::max<int64_t>(g, 1));
 }
