@@ -533,7 +533,8 @@ static int ensure_scan_counters(tav_index* ix, cudaStream_t s) {
 // Row-scan search of nq_total queries (device float32), any k: passes of <= kPassK hits.
 static int scan_search(tav_index* ix, TimedSearch* ts, bool timing, const float* d_queries, int nq_total, int k, float floor_score,
                        const int64_t* d_subset, int64_t n_scan, int64_t item_offset, int64_t* d_items,
-                       float* d_scores, int32_t* d_counts, const uint32_t* d_mask, int ties_low, cudaStream_t s) {
+                       float* d_scores, int32_t* d_counts, const uint32_t* d_mask, int ties_low, cudaStream_t s,
+                       bool allow_fuse = true) {
     const int pass_k = std::min(k, kPassK);
     int qb = scan_max_queries(ix->dim, pass_k);
     if (qb < 1) {
@@ -543,13 +544,19 @@ static int scan_search(tav_index* ix, TimedSearch* ts, bool timing, const float*
     qb = std::min(qb, nq_total);
     // round qb down to a power of two (kernel instantiations 1/2/4/8)
     while (qb & (qb - 1)) qb &= qb - 1;
-    const int grid = scan_grid(ix->device, ix->dtype, ix->dim, qb, pass_k, n_scan);
-    const int cand_stride = grid * pass_k;
+    int grid = scan_grid(ix->device, ix->dtype, ix->dim, qb, pass_k, n_scan);
+    const int n_pass = (k + pass_k - 1) / pass_k;
+    // L2-sized scans with a small k end in the scan kernel itself: its last CTA merges the survivors of all
+    // CTAs and writes the hits (no select launch) — the device-query twin of the single-launch latency form
+    const bool fuse = allow_fuse && n_pass == 1 && pass_k <= 64 &&
+                      static_cast<size_t>(n_scan) * ix->dim * dtype_size(ix->dtype) <= kFusedScanMaxBytes &&
+                      static_cast<int64_t>(std::min(grid, 148)) * std::max(pass_k, 32) <= kFusedSelectMax;
+    if (fuse) grid = std::min(grid, kFusedSelectMax / std::max(pass_k, 32));
+    const int cand_stride = grid * (fuse ? std::max(pass_k, 32) : pass_k);
     TAV_CUDA(ix->cand_keys.ensure(static_cast<size_t>(qb) * cand_stride * sizeof(uint64_t)));
     if (int rc = ensure_scan_counters(ix, s)) return rc;
     uint64_t* d_bound = static_cast<uint64_t*>(ix->cand_count.p);
     uint32_t* d_count = reinterpret_cast<uint32_t*>(d_bound + 8);
-    const int n_pass = (k + pass_k - 1) / pass_k;
 
     for (int q0 = 0; q0 < nq_total; q0 += qb) {
         const int nq = std::min(qb, nq_total - q0);
@@ -573,12 +580,24 @@ static int scan_search(tav_index* ix, TimedSearch* ts, bool timing, const float*
             a.grid = grid;
             a.row_mask = d_mask;
             a.ties_low = ties_low;
+            if (fuse) {
+                a.fused = 1;
+                a.fused_ticket = d_count + 8;
+                a.item_offset = item_offset;
+                a.out_items = d_items + static_cast<size_t>(q0) * k;
+                a.out_scores = d_scores + static_cast<size_t>(q0) * k;
+                a.out_counts = d_counts + q0;
+            }
             const bool timed = timing && ts && ts->used < kMaxTimedKernels;
             if (timed) TAV_CUDA(ev_record(ts->ev[ts->used][0], s));
             TAV_CUDA(launch_scan(a, s));
             if (timed) {
                 ts->kind[ts->used] = 0;
                 TAV_CUDA(ev_record(ts->ev[ts->used++][1], s));
+            }
+            if (fuse) {
+                if (ts) ts->launches += 1;
+                continue;
             }
             SelectArgs sel{};
             sel.cand_keys = a.cand_keys;
@@ -1064,7 +1083,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
     } else {
         ts->path = 1;
         int rc = scan_search(ix, ts, timing, d_queries, n_queries, k, min_score, d_subset, n_scan, item_offset,
-                             d_items, d_scores, d_counts, d_mask, ties_low, s);
+                             d_items, d_scores, d_counts, d_mask, ties_low, s, !(flags & TAV_NO_FUSED_SCAN));
         if (rc != TAV_OK) return rc;
     }
     if (timing) {

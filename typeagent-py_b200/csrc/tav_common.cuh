@@ -120,6 +120,57 @@ __device__ __forceinline__ int warp_topk_small(uint64_t* keys, int n, int k) {
     return out;
 }
 
+// The k largest (k <= 32) of `total` <= 8 * 32 * R unsorted keys in shared memory, by the 8 warps of a
+// 256-thread CTA, without a sort: every warp extracts the k largest of its slice of 32 * R keys (R registers
+// per lane, k rounds of a shuffle arg-max), then warp 0 does the same over the 8 x k finalists.  Two CTA
+// barriers in all.  `scratch` needs 8 * 32 + 32 slots; returns a pointer to min(total, k) keys, descending.
+template <int R>
+__device__ __forceinline__ void warp_extract_top(uint64_t (&r)[R], int rounds, uint64_t* dst, int lane) {
+    for (int i = 0; i < rounds; ++i) {
+        uint64_t m = r[0];
+#pragma unroll
+        for (int j = 1; j < R; ++j) m = r[j] > m ? r[j] : m;
+        uint64_t w = m;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, w, off);
+            w = o > w ? o : w;
+        }
+        if (m == w && w != 0) {  // unique keys: exactly one lane, one register, owns the maximum
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+                if (r[j] == w) r[j] = 0;
+        }
+        if (lane == 0) dst[i] = w;
+    }
+}
+
+template <int R>
+__device__ __forceinline__ const uint64_t* block_topk_small(const uint64_t* keys, int total, int k, uint64_t* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        uint64_t r[R];
+        const int base = warp * 32 * R;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int i = base + lane + 32 * j;
+            r[j] = i < total ? keys[i] : 0;
+        }
+        warp_extract_top<R>(r, k, scratch + warp * 32, lane);
+        if (lane >= k) scratch[warp * 32 + lane] = 0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = scratch[lane + 32 * j];
+        __syncwarp();
+        warp_extract_top<8>(r, k, scratch + 256, lane);
+    }
+    __syncthreads();
+    return scratch + 256;
+}
+
 // returns 1 when the list is now above `watermark` (compaction needed before the next round)
 __device__ __forceinline__ int list_push(CandList l, uint64_t key, int watermark) {
     const int slot = atomicAdd(l.count, 1);

@@ -363,7 +363,12 @@ scan_rows_kernel(const ScanArgs a, const __grid_constant__ BLOB blob) {
             uint32_t* hist = reinterpret_cast<uint32_t*>(sel_out + kFusedSelOut);
             const uint64_t* result = keys;
             int n = -1;
-            if (total > 256 && a.k <= kFusedSelOut / 2) {
+            if (a.k <= 32 && total <= 4096) {
+                // the latency case (few survivors, small k): warp-level arg-max rounds, no sort, two barriers
+                result = total <= 2048 ? block_topk_small<8>(keys, total, a.k, sel_out)
+                                       : block_topk_small<16>(keys, total, a.k, sel_out);
+                n = min(total, a.k);
+            } else if (total > 256 && a.k <= kFusedSelOut / 2) {
                 const int got = select_topk_smem<kScanThreads>(keys, total, a.k, hist, sel_out, kFusedSelOut);
                 if (got >= 0) {
                     n = min(got, a.k);
