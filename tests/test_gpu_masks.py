@@ -133,7 +133,8 @@ def test_single_launch_form_matches_the_two_kernel_form_and_the_oracle():
         sub = list(range(0, n, 3)) + [0, -1]
         assert_hits_match(one.fuzzy_lookup_embedding_in_subset(q[0], sub, k, 0.0),
                           O.lookup_in_subset(v, q[0], sub, k, 0.0), what="subset in the kernel parameters")
-        assert one.last_timing()["launches"] == (1 if len(sub) <= 4096 else 2)   # short subsets ride in the parameters
+        assert one.last_timing()["launches"] == 1   # short subsets ride in the parameters; longer ones are uploaded,
+        #                                               but an L2-sized scan still ends in the scan kernel itself
         with pytest.raises(IndexError):
             one.fuzzy_lookup_embedding_in_subset(q[0], [0, n], k, 0.0)
 
