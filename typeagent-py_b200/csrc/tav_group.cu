@@ -8,9 +8,12 @@
 // PUBLISH kernel stores this rank's packed list straight into every peer's region over NVLink (plain
 // st.global on peer-mapped pointers) and raises a sequence flag with a system-scope release; the MERGE
 // kernel of every rank spins (acquire) until all ranks' flags reached the search's sequence number,
-// merges the world's lists from its own HBM and acknowledges to the peers, so that a slot is never
-// overwritten while a slower rank still reads it.  One process per GPU; the handles travel once,
-// through whatever the host side has (torch.distributed.all_gather_object in the Python class).
+// merges the world's lists from its own HBM and — its last CTA — acknowledges to the peers, so that a
+// slot is never overwritten while a slower rank still reads it: two launches per exchange, no NCCL call,
+// no host synchronisation.  Pipelined (TAV_DEFER_RETRY) searches run the exchange on the group's own
+// stream behind an event, so that the next search's kernels do not queue behind the wait for the slowest
+// rank.  One process per GPU; the handles travel once, through whatever the host side has
+// (torch.distributed.all_gather_object in the Python class).
 //
 // Region layout (device memory of the owning rank):
 //   arrive[world]  u32   arrive[r] = sequence number of the last search rank r PUBLISHED here

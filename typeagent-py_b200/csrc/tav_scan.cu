@@ -307,10 +307,12 @@ scan_rows_kernel(const ScanArgs a, const __grid_constant__ BLOB blob) {
         // goes over unsorted (the last CTA selects anyway).  Otherwise the k best are extracted — by one warp
         // with shuffles when the list is short and k small (no CTA barriers), else by the bitonic compaction.
         const int keep_all = (a.fused && static_cast<int64_t>(gridDim.x) * kRoundRows <= 2048) ? max(a.k, kRoundRows) : a.k;
-        if (s_cnt[q] > keep_all) {  // CTA-uniform
-            if (a.k <= 32 && s_cnt[q] <= 128) {
+        const int have = s_cnt[q];  // read by every thread BEFORE warp 0 may rewrite it (racecheck: the branch below
+        __syncthreads();            // must see one value in all warps, or the barriers inside it diverge)
+        if (have > keep_all) {      // CTA-uniform
+            if (a.k <= 32 && have <= 128) {
                 if (warp == 0) {
-                    const int kept = warp_topk_small(l.keys, s_cnt[q], a.k);
+                    const int kept = warp_topk_small(l.keys, have, a.k);
                     if (lane == 0) s_cnt[q] = kept;
                 }
                 __syncthreads();
