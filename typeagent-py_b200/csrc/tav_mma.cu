@@ -19,21 +19,24 @@
 //              CTAs) and publishes the accumulator.
 //   warps 2-9  epilogue: tcgen05.ld 32 lanes x 32 columns, double-buffered in registers — a
 //              thread owns ONE query (its TMEM lane) and half of the tile's 256 rows.  Per
-//              32-row chunk it takes the max of the 32 dots (branch-free) and compares it with
-//              the query's admission threshold; only chunks that contain an admitted row take
-//              the slow path (branch-free mask, one atomicAdd per lane, predicated stores of
-//              (dot, row) pairs into the query's global candidate buffer).  Runs concurrently
-//              with the next tile's MMAs (two TMEM stages).
+//              32-row chunk: the maximum of each group of 8 dots against the query's admission
+//              threshold; only a group that holds an admitted row runs its 8 predicated
+//              compare-and-append steps, (dot, row) keys going to the thread's PRIVATE segment
+//              of the query's candidate buffer (register counter, no atomics; admit_chunk).
+//              Runs concurrently with the next tile's MMAs (two TMEM stages).
+// For embedding sizes up to 768 and more than 128 queries the MAIN pass runs in the Q-stationary
+// form instead (mma_ts_main_kernel below): the query block lives in tensor memory.
 //
 // Work items are (corpus tile, query chunk) pairs — a chunk is 128 queries (single CTA) or 256
-// (CTA pair) — so ANY number of queries is served by ONE launch per pass: the chunks of a tile
-// are visited by neighbouring units at the same time and share the tile through L2, i.e. HBM is
-// read once per search, not once per 256 queries.
+// (CTA pair) — so ANY number of queries is served by ONE launch per pass: a unit serves one chunk
+// and every n-th tile, the chunks of a tile are visited by neighbouring units at the same time
+// and share the tile through L2, i.e. HBM is read once per search, not once per 256 queries.
 //
 // Admission thresholds.  A first launch of the same kernel in SAMPLE mode scores a strided sample
-// of corpus tiles; its epilogue is branch-free: every thread only keeps the maximum of the 128
-// dots it sees per tile ("block maximum") and stores it.  The CTA that finishes a query chunk's
-// last sample tile then derives, per query, the 8th largest block maximum — at least 8 distinct
+// of corpus tiles; its epilogue is branch-free: every thread only keeps the maxima of blocks of
+// the dots it sees (128 rows = a tile half for large corpora; 32 or 8 rows when the target is a
+// larger share of the corpus) and stores them.  The unit that finishes a query chunk's last
+// sample tile then derives, per query, the 8th largest block maximum — at least 8 distinct
 // rows reach it — lowers it to the bottom of its float32 score class, never below the caller's
 // min_score, and publishes it as the admission threshold (expected to admit `target` rows of the
 // corpus, see make_plan).  The MAIN launch then streams the whole corpus once; a finalize kernel
