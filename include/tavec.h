@@ -211,7 +211,9 @@ int tav_mma_scores(tav_index* ix, const float* queries, int n_queries, int flags
                    void* stream);
 
 /* Event timing is off by default (four fewer driver calls per search); enable it before the
- * searches you want timed.  Path and launch count are always recorded. */
+ * searches you want timed: 1 = an event pair around every kernel, 2 = only around the dominant
+ * kernel and the whole search (the pairs themselves cost ~1-2 us of device time per kernel
+ * boundary).  Path and launch count are always recorded. */
 int tav_set_timing(tav_index* ix, int enabled);
 
 /* Device time of the last tav_search on this index, measured with CUDA events on the

@@ -172,6 +172,7 @@ struct tav_index {
     int64_t search_seq = 0;      // searches timed so far
     TimedSearch untimed;         // path / launch count of the last search when timing is off
     bool timing_on = false;
+    bool timing_light = false;  // events only around the dominant kernel and the whole search
 };
 
 static TimedSearch* cur_timed(tav_index* ix) {
@@ -1058,6 +1059,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
             m.ev_kind = ts->kind;
             m.ev_max = kMaxTimedKernels;
             m.ev_used = &ev_used;
+            m.ev_main_only = ix->timing_light ? 1 : 0;
             const size_t ws = mma_workspace_bytes(m);
             if (ws > ix->mma_ws.bytes) {
                 TAV_CUDA(cudaStreamSynchronize(s));  // earlier searches may still use the old workspace
@@ -1201,6 +1203,7 @@ int tav_set_timing(tav_index* ix, int enabled) {
     if (!ix) return TAV_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ix->mu);
     ix->timing_on = enabled != 0;
+    ix->timing_light = enabled == 2;
     if (ix->timing_on && !ix->hist) {
         ix->hist = new (std::nothrow) TimedSearch[kHistory];
         if (!ix->hist) return TAV_ERR_OOM;

@@ -125,6 +125,7 @@ struct MmaArgs {
     int* ev_kind;          //   kind per pair: 0 = dominant (MAIN) kernel, 1 = sample pass, 2 = auxiliary
     int ev_max;
     int* ev_used;
+    int ev_main_only;      // 1: record events only around the dominant (MAIN) kernel
 };
 constexpr int kMmaMaxQueries = 32768;  // queries per launch_mma_search call (512 chunks of >= 128 ... callers slab)
 size_t mma_workspace_bytes(const MmaArgs& a);

@@ -1246,11 +1246,16 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
     uint64_t* d_cand = reinterpret_cast<uint64_t*>(ws + p.off_cand);
     int n_launch = 0, ev_used = 0;
     cudaError_t e;
-    auto ev_begin = [&]() -> cudaError_t {
-        return (a.ev && ev_used < a.ev_max) ? cudaEventRecord(a.ev[ev_used][0], s) : cudaSuccess;
+    // event pairs around the kernels: all of them, or (ev_main_only) only around the dominant kernel — two
+    // event records per kernel boundary are a measurable share of a 0.1-0.4 ms search
+    bool ev_open = false;
+    auto ev_begin_kind = [&](int kind) -> cudaError_t {
+        ev_open = a.ev && ev_used < a.ev_max && (!a.ev_main_only || kind == 0);
+        return ev_open ? cudaEventRecord(a.ev[ev_used][0], s) : cudaSuccess;
     };
     auto ev_end = [&](int kind) -> cudaError_t {
-        if (!(a.ev && ev_used < a.ev_max)) return cudaSuccess;
+        if (!ev_open) return cudaSuccess;
+        ev_open = false;
         if (a.ev_kind) a.ev_kind[ev_used] = kind;
         return cudaEventRecord(a.ev[ev_used++][1], s);
     };
@@ -1261,7 +1266,7 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
     if (!build_maps(a, d_q, d_q_lo, p.nq_pad, p.ts ? p.tile_n / 2 : 0, maps, &map_ts)) return cudaErrorUnknown;
 
     // queries -> storage dtype; without a sample pass this launch also initialises thresholds / counters
-    if ((e = ev_begin()) != cudaSuccess) return e;
+    if ((e = ev_begin_kind(2)) != cudaSuccess) return e;
     e = prep_queries(a, d_q, d_q_lo, p.nq_pad, p.n_sample == 0 ? 1 : 0, d_thr, d_floor, s);
     if (e != cudaSuccess) return e;
     if ((e = ev_end(2)) != cudaSuccess) return e;
@@ -1295,7 +1300,7 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
         ka.n_tiles_work = p.n_sample;
         ka.tile_mul = p.n_full_tiles;
         ka.tile_div = p.n_sample;
-        if ((e = ev_begin()) != cudaSuccess) return e;
+        if ((e = ev_begin_kind(1)) != cudaSuccess) return e;
         e = launch_kernel<kSample>(maps, ka, p.cg, kdt, split, p.sample_units, s);
         if (e != cudaSuccess) return e;
         if ((e = ev_end(1)) != cudaSuccess) return e;
@@ -1305,7 +1310,7 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
     ka.n_tiles_work = p.n_main_tiles;
     ka.tile_mul = 1;
     ka.tile_div = 1;
-    if ((e = ev_begin()) != cudaSuccess) return e;
+    if ((e = ev_begin_kind(0)) != cudaSuccess) return e;
     if (p.ts) {
         // Q-stationary form: query block in tensor memory, corpus slabs through shared memory
         TsArgs ta{};
@@ -1349,7 +1354,7 @@ cudaError_t launch_mma_search(const MmaArgs& a, void* workspace, size_t workspac
     static int finalize_granted[16] = {};
     e = ensure_dynamic_smem(finalize_kernel, sel_smem, finalize_granted);
     if (e != cudaSuccess) return e;
-    if ((e = ev_begin()) != cudaSuccess) return e;
+    if ((e = ev_begin_kind(2)) != cudaSuccess) return e;
     finalize_kernel<<<a.nq, kSelectThreads, sel_smem, s>>>(d_cand, d_count, p.n_seg, p.cap_seg, fast_cap, d_thr, d_floor,
                                                            a.k, a.item_offset, a.out_items, a.out_scores,
                                                            a.out_counts, a.retry_flags, a.retry_total, a.retry_total_host);

@@ -297,7 +297,7 @@ class VectorBase:
             self._ix_generation = -1
             self._ix_rows = 0
             if self._timing:
-                _capi.check(lib.tav_set_timing(self._ix, 1))
+                _capi.check(lib.tav_set_timing(self._ix, int(self._timing)))
         if self._device_only_rows:
             return lib, self._ix
         if self._ix_generation != self._generation:
@@ -429,11 +429,12 @@ class VectorBase:
         )
         return items, scores, counts
 
-    def enable_timing(self, enabled: bool = True) -> None:
-        """Record CUDA events around the kernels of subsequent lookups (see ``last_timing``)."""
-        self._timing = bool(enabled)
+    def enable_timing(self, enabled: bool = True, main_only: bool = False) -> None:
+        """Record CUDA events around the kernels of subsequent lookups (see ``last_timing``);
+        ``main_only``: just the dominant kernel and the whole search (cheaper)."""
+        self._timing = (2 if main_only else 1) if enabled else 0
         if self._ix is not None:
-            _capi.check(_capi.load().tav_set_timing(self._ix, 1 if enabled else 0))
+            _capi.check(_capi.load().tav_set_timing(self._ix, self._timing))
 
     def last_timing(self) -> dict:
         """Path, launch count and — after ``enable_timing()`` — device times of the last lookup
