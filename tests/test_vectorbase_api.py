@@ -228,3 +228,19 @@ def test_product_package_never_imports_the_oracle():
                 with open(os.path.join(dirpath, name)) as f:
                     text = f.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), name
+
+
+def test_host_helper_packs_int_lists_and_declines_everything_else():
+    """libtavhost.so (csrc/tav_pyhost.c) only short-cuts `list[int] -> int64 buffer` for
+    fuzzy_lookup_embedding_in_subset; anything else must be declined (-1) so that the generic numpy
+    conversion — which raises the reference's errors — handles it."""
+    pack = _capi.pack_int_list()
+    if pack is None:
+        pytest.skip("libtavhost.so not built (no Python.h / gcc)")
+    buf = np.full(8, -7, np.int64)
+    assert pack([3, 0, -5, 2**62], buf.ctypes.data, 8) == 4
+    assert buf[:4].tolist() == [3, 0, -5, 2**62] and buf[4] == -7
+    assert pack([], buf.ctypes.data, 8) == 0
+    for declined in ([1, True], (1, 2), [1, 2**70], [1.0], [np.int64(3)], "ab", None):
+        assert pack(declined, buf.ctypes.data, 8) == -1
+    assert pack(list(range(9)), buf.ctypes.data, 8) == -2

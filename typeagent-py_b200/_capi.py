@@ -100,6 +100,28 @@ def load() -> C.CDLL:
     return _lib
 
 
+HOST_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtavhost.so")
+_pack_int_list = False  # False = not probed yet, None = unavailable
+
+
+def pack_int_list():
+    """`tavhost_pack_int_list(list, int64* out, cap) -> n | -1 | -2` from libtavhost.so (csrc/tav_pyhost.c),
+    or None when that optional helper was not built.  Host-side convenience only (a Python list of
+    ordinals -> int64 buffer in 4 us instead of 18 us); it is not on the compute path."""
+    global _pack_int_list
+    if _pack_int_list is False:
+        fn = None
+        if os.path.exists(HOST_LIB_PATH):
+            try:
+                fn = C.PyDLL(HOST_LIB_PATH).tavhost_pack_int_list
+                fn.restype = C.c_longlong
+                fn.argtypes = [C.py_object, C.c_void_p, C.c_longlong]
+            except (OSError, AttributeError):
+                fn = None
+        _pack_int_list = fn
+    return _pack_int_list
+
+
 def last_error() -> str:
     msg = load().tav_last_error()
     return msg.decode("utf-8", "replace") if msg else ""

@@ -126,6 +126,7 @@ class VectorBase:
         self._device_only_rows = 0  # rows living only on the device (from_device_tensor)
         self._adopted_tensor = None
         self._single_out: dict[int, tuple] = {}  # k -> reusable result arrays of fuzzy_lookup_embedding
+        self._subset_buf: np.ndarray | None = None  # reusable int64 buffer for list subsets
         self.force_path: str | None = None  # "scan" | "mma" | "scan2" (two-kernel scan) | None (tests / benchmarks)
         self._timing = False
         self._pending: list = []             # tensors of deferred device searches, kept alive until finish_search()
@@ -504,10 +505,19 @@ class VectorBase:
         sub_ptr, sub_len, sub = None, 0, None
         if subset is not None:
             if type(subset) is list:
-                try:
-                    sub = np.frombuffer(_array("q", subset), dtype=np.int64)   # ~4x faster than np.asarray(list)
-                except (TypeError, OverflowError):
-                    sub = None
+                pack = _capi.pack_int_list()
+                if pack is not None:                 # CPython-API walk of the list: 4 us per 1000 ordinals
+                    buf = self._subset_buf
+                    if buf is None or len(buf) < len(subset):
+                        buf = self._subset_buf = np.empty(max(4096, 2 * len(subset)), np.int64)
+                    got = pack(subset, buf.ctypes.data, len(buf))
+                    if got >= 0:
+                        sub = buf[:got]
+                if sub is None:
+                    try:
+                        sub = np.frombuffer(_array("q", subset), dtype=np.int64)   # 18 us; np.asarray(list): 29 us
+                    except (TypeError, OverflowError):
+                        sub = None
             if sub is None:
                 sub = np.ascontiguousarray(subset)
                 if sub.size and not np.issubdtype(sub.dtype, np.integer):
