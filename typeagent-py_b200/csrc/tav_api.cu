@@ -920,7 +920,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
             cudaStreamSynchronize(s);
             static int printed = 0;
             if (++printed % 500 == 0)
-                fprintf(stderr, "[tav trace] grid %d: staged +%.1f us, scanned +%.1f, handed +%.1f, merge starts +%.1f, hits "
+                fprintf(stderr, "[tav trace] grid %d: staged +%.1f us, scanned +%.1f, handed +%.1f (CTA 0) | last CTA: merge starts at %.1f, hits "
                                 "written +%.1f, flag +%.1f (kernel %.1f us) | host call until flag seen %.1f us\n", a.grid,
                         (trace_host[1] - trace_host[0]) / 1e3, (trace_host[2] - trace_host[1]) / 1e3,
                         (trace_host[3] - trace_host[2]) / 1e3, (trace_host[4] - trace_host[0]) / 1e3,

@@ -74,10 +74,92 @@ struct CandList {
     uint64_t* admit; // keys >= *admit are admitted
 };
 
+// ---- rank selection: the k best of a SHORT unsorted list without sorting it ------------------------------
+// The owner of a key counts the keys greater than it (broadcast reads of shared memory).  Keys are unique,
+// so the counts are a permutation and a key of rank < k belongs at out[rank].  O(n^2 / lanes) compares but
+// no dependent shuffle chains and next to no barriers: for the <= 256-key lists of the latency path this
+// costs a few hundred cycles where a bitonic sort of 128 slots costs 28 CTA barriers (~3 us) and k rounds
+// of a shuffle arg-max ~2 us.
+__device__ __forceinline__ int rank_among(const uint64_t* in, int n, uint64_t mine) {
+    int rank = 0, i = 0;
+    for (; i + 2 <= n; i += 2) {  // `in` is 16-byte aligned: one LDS.128 per two keys
+        const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(in + i);
+        rank += (p.x > mine) + (p.y > mine);
+    }
+    if (i < n) rank += in[i] > mine;
+    return rank;
+}
+
+// One warp: the min(n, k) largest of n <= 64 keys, descending, into out (which must not overlap in[0..n)).
+__device__ __forceinline__ void warp_rank_select(const uint64_t* in, int n, int k, uint64_t* out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t m0 = lane < n ? in[lane] : 0, m1 = lane + 32 < n ? in[lane + 32] : 0;
+    int r0 = 0, r1 = 0, i = 0;
+    for (; i + 2 <= n; i += 2) {
+        const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(in + i);
+        r0 += (p.x > m0) + (p.y > m0);
+        r1 += (p.x > m1) + (p.y > m1);
+    }
+    if (i < n) {
+        const uint64_t o = in[i];
+        r0 += o > m0;
+        r1 += o > m1;
+    }
+    if (lane < n && r0 < k) out[r0] = m0;
+    if (lane + 32 < n && r1 < k) out[r1] = m1;
+}
+
+// The k (<= 32) largest of `total` <= 4096 unique keys at keys[0..total), by a 256-thread CTA: levels of
+// 64-key slices, each reduced to its k best by one warp, until <= 256 keys are left for one CTA-wide rank
+// selection.  Every slice but the last is full (64 >= k keys), so the slices' outputs are dense and the next
+// level needs no padding.  keys[] must have room for 8192 entries (upper half = ping-pong buffer) and is
+// clobbered; callers barrier before (keys filled); out[0..min(total, k)) is valid after the call.
+__device__ __forceinline__ void block_rank_topk(uint64_t* keys, int total, int k, uint64_t* out) {
+    const int warp = threadIdx.x >> 5;
+    uint64_t* in = keys;
+    uint64_t* tmp = keys + 4096;
+    int n = total;
+    while (n > kSelectThreads) {
+        const int slices = (n + 63) >> 6;
+        for (int s = warp; s < slices; s += kSelectThreads / 32)
+            warp_rank_select(in + 64 * s, min(64, n - 64 * s), k, tmp + s * k);
+        __syncthreads();
+        n = (slices - 1) * k + min(n - 64 * (slices - 1), k);
+        uint64_t* t = in;
+        in = tmp;
+        tmp = t;
+    }
+    if (static_cast<int>(threadIdx.x) < n) {
+        const uint64_t mine = in[threadIdx.x];
+        const int rank = rank_among(in, n, mine);
+        if (rank < k) out[rank] = mine;
+    }
+    __syncthreads();
+}
+
 template <int THREADS>
 __device__ __forceinline__ void list_compact(CandList l, int cap, int k, uint64_t floor_key) {
     // all threads call; *l.count is stable (callers barrier first)
     const int n = min(*l.count, cap);
+    if (cap <= THREADS) {
+        // short list (one key per thread): rank selection in place, three barriers
+        uint64_t mine = 0;
+        int rank = k;
+        if (static_cast<int>(threadIdx.x) < n) {
+            mine = l.keys[threadIdx.x];
+            rank = rank_among(l.keys, n, mine);
+        }
+        __syncthreads();  // every key is in a register, every rank counted
+        if (rank < k) l.keys[rank] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int kept = min(n, k);
+            *l.count = kept;
+            *l.admit = (kept == k) ? l.keys[k - 1] + 1 : floor_key;
+        }
+        __syncthreads();
+        return;
+    }
     for (int i = n + threadIdx.x; i < cap; i += THREADS) l.keys[i] = 0;
     bitonic_sort_desc<THREADS>(l.keys, cap);
     if (threadIdx.x == 0) {
@@ -86,89 +168,6 @@ __device__ __forceinline__ void list_compact(CandList l, int cap, int k, uint64_
         *l.admit = (kept == k) ? l.keys[k - 1] + 1 : floor_key;
     }
     __syncthreads();
-}
-
-// The k largest of n <= 128 keys in shared memory, k <= 32, by ONE warp: every lane holds up to four keys
-// in registers and the warp extracts the maximum k times (shuffle reduction; keys are unique).  No CTA
-// barriers — list_compact's bitonic sort of 128 slots costs 28 of them (~3 us) for the same job.
-// Called by warp 0 only; keys[0..k) receive the result in descending order, returns min(n, k).
-__device__ __forceinline__ int warp_topk_small(uint64_t* keys, int n, int k) {
-    const int lane = threadIdx.x & 31;
-    uint64_t r[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) r[j] = lane + 32 * j < n ? keys[lane + 32 * j] : 0;
-    __syncwarp();
-    const int out = min(n, k);
-    for (int i = 0; i < out; ++i) {
-        uint64_t m = r[0] > r[1] ? r[0] : r[1];
-        const uint64_t m2 = r[2] > r[3] ? r[2] : r[3];
-        m = m > m2 ? m : m2;
-        uint64_t w = m;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, w, off);
-            w = o > w ? o : w;
-        }
-        if (m == w && w != 0) {  // the owner retires it (unique keys: exactly one lane, one register)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (r[j] == w) r[j] = 0;
-        }
-        if (lane == 0) keys[i] = w;
-    }
-    __syncwarp();
-    return out;
-}
-
-// The k largest (k <= 32) of `total` <= 8 * 32 * R unsorted keys in shared memory, by the 8 warps of a
-// 256-thread CTA, without a sort: every warp extracts the k largest of its slice of 32 * R keys (R registers
-// per lane, k rounds of a shuffle arg-max), then warp 0 does the same over the 8 x k finalists.  Two CTA
-// barriers in all.  `scratch` needs 8 * 32 + 32 slots; returns a pointer to min(total, k) keys, descending.
-template <int R>
-__device__ __forceinline__ void warp_extract_top(uint64_t (&r)[R], int rounds, uint64_t* dst, int lane) {
-    for (int i = 0; i < rounds; ++i) {
-        uint64_t m = r[0];
-#pragma unroll
-        for (int j = 1; j < R; ++j) m = r[j] > m ? r[j] : m;
-        uint64_t w = m;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, w, off);
-            w = o > w ? o : w;
-        }
-        if (m == w && w != 0) {  // unique keys: exactly one lane, one register, owns the maximum
-#pragma unroll
-            for (int j = 0; j < R; ++j)
-                if (r[j] == w) r[j] = 0;
-        }
-        if (lane == 0) dst[i] = w;
-    }
-}
-
-template <int R>
-__device__ __forceinline__ const uint64_t* block_topk_small(const uint64_t* keys, int total, int k, uint64_t* scratch) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    {
-        uint64_t r[R];
-        const int base = warp * 32 * R;
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-            const int i = base + lane + 32 * j;
-            r[j] = i < total ? keys[i] : 0;
-        }
-        warp_extract_top<R>(r, k, scratch + warp * 32, lane);
-        if (lane >= k) scratch[warp * 32 + lane] = 0;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        uint64_t r[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = scratch[lane + 32 * j];
-        __syncwarp();
-        warp_extract_top<8>(r, k, scratch + 256, lane);
-    }
-    __syncthreads();
-    return scratch + 256;
 }
 
 // returns 1 when the list is now above `watermark` (compaction needed before the next round)

@@ -21,6 +21,12 @@ long long tavhost_pack_int_list(PyObject* list, long long* out, long long cap)
     for (Py_ssize_t i = 0; i < n; ++i) {
         PyObject* item = PyList_GET_ITEM(list, i);
         if (!PyLong_CheckExact(item)) return -1;
+#if PY_VERSION_HEX >= 0x030C0000
+        if (PyUnstable_Long_IsCompact((const PyLongObject*)item)) {  /* one digit: no call, no overflow */
+            out[i] = (long long)PyUnstable_Long_CompactValue((const PyLongObject*)item);
+            continue;
+        }
+#endif
         int overflow = 0;
         const long long v = PyLong_AsLongLongAndOverflow(item, &overflow);
         if (overflow) return -1;

@@ -21,6 +21,7 @@
 
 #include "tav_common.cuh"
 #include "tav_internal.h"
+#include <cstdlib>
 
 namespace tav {
 
@@ -303,23 +304,11 @@ scan_rows_kernel(const ScanArgs a, const __grid_constant__ BLOB blob) {
     for (int q = 0; q < QB; ++q) {
         if (q >= a.nq) break;
         CandList l{skeys + static_cast<size_t>(q) * cap, &s_cnt[q], &s_admit[q]};
-        // Hand over the CTA's best k.  Single-launch form on a small grid: up to one round's worth of keys
-        // goes over unsorted (the last CTA selects anyway).  Otherwise the k best are extracted — by one warp
-        // with shuffles when the list is short and k small (no CTA barriers), else by the bitonic compaction.
-        const int keep_all = (a.fused && static_cast<int64_t>(gridDim.x) * kRoundRows <= 2048) ? max(a.k, kRoundRows) : a.k;
-        const int have = s_cnt[q];  // read by every thread BEFORE warp 0 may rewrite it (racecheck: the branch below
-        __syncthreads();            // must see one value in all warps, or the barriers inside it diverge)
-        if (have > keep_all) {      // CTA-uniform
-            if (a.k <= 32 && have <= 128) {
-                if (warp == 0) {
-                    const int kept = warp_topk_small(l.keys, have, a.k);
-                    if (lane == 0) s_cnt[q] = kept;
-                }
-                __syncthreads();
-            } else {
-                list_compact<kScanThreads>(l, cap, a.k, floor_key);
-            }
-        }
+        // Hand over the CTA's best k (rank selection when the list is short: three barriers, no sort), so that
+        // the last CTA of the single-launch form merges grid * k keys and not grid * (a round's worth).
+        const int have = s_cnt[q];  // read by every thread BEFORE thread 0 may rewrite it (racecheck: the branch
+        __syncthreads();            // below must see one value in all warps, or the barriers inside it diverge)
+        if (have > a.k) list_compact<kScanThreads>(l, cap, a.k, floor_key);  // CTA-uniform
         const int n = s_cnt[q];
         if (tid == 0 && n > 0) s_base[q] = atomicAdd(&a.cand_count[q], static_cast<uint32_t>(n));
         __syncthreads();
@@ -366,9 +355,9 @@ scan_rows_kernel(const ScanArgs a, const __grid_constant__ BLOB blob) {
             const uint64_t* result = keys;
             int n = -1;
             if (a.k <= 32 && total <= 4096) {
-                // the latency case (few survivors, small k): warp-level arg-max rounds, no sort, two barriers
-                result = total <= 2048 ? block_topk_small<8>(keys, total, a.k, sel_out)
-                                       : block_topk_small<16>(keys, total, a.k, sel_out);
+                // the latency case (few survivors, small k): levels of rank selection, no sort
+                block_rank_topk(keys, total, a.k, sel_out);
+                result = sel_out;
                 n = min(total, a.k);
             } else if (total > 256 && a.k <= kFusedSelOut / 2) {
                 const int got = select_topk_smem<kScanThreads>(keys, total, a.k, hist, sel_out, kFusedSelOut);
@@ -481,10 +470,18 @@ int scan1_grid(int device, int dim, int k, int64_t n_scan) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     int64_t tiles = (n_scan + kRoundRows - 1) / kRoundRows;
-    // up to 4 CTAs per SM (the general form's occupancy); the last CTA's merge cost does not grow with the
-    // number of survivors (histogram selection), only its buffer bounds the grid
-    int64_t g = std::min<int64_t>(tiles, 4ll * sms);    // one round of rows per CTA while the rows last
-    g = std::min<int64_t>(g, kFusedSelectMax / std::max(k, 1));
+    // up to 4 CTAs per SM (the general form's occupancy), one round of rows per CTA while the rows last.  The
+    // last CTA merges grid * k survivors: its buffer bounds the grid, and for the rank-selection merge (k <= 32,
+    // ~2.3 us per 1000 survivors) so does its cost — measured on 10k x 384, k = 10 (profiles/r02_latency_grid_sweep.log):
+    // 2048 survivors (204 CTAs, two rounds each) beats 8192 (313 CTAs, one round) by 4.7 us and 512 by 4.2 us.
+    int64_t g = std::min<int64_t>(tiles, 4ll * sms);
+    static const int64_t survivors_env = [] {
+        const char* e = getenv("TAV_SCAN1_SURVIVORS");  // tuning knob for that sweep
+        return e ? std::max<int64_t>(atoll(e), 0) : 0;
+    }();
+    int64_t survivors_max = k <= 32 ? 2048 : kFusedSelectMax;
+    if (survivors_env > 0) survivors_max = std::min<int64_t>(survivors_env, kFusedSelectMax);
+    g = std::min<int64_t>(g, survivors_max / std::max(k, 1));
     (void)dim;
     return static_cast<int>(std::max<int64_t>(g, 1));
 }

@@ -126,7 +126,7 @@ class VectorBase:
         self._device_only_rows = 0  # rows living only on the device (from_device_tensor)
         self._adopted_tensor = None
         self._single_out: dict[int, tuple] = {}  # k -> reusable result arrays of fuzzy_lookup_embedding
-        self._subset_buf: np.ndarray | None = None  # reusable int64 buffer for list subsets
+        self._subset_buf: tuple | None = None  # (reusable int64 buffer for list subsets, its address)
         self.force_path: str | None = None  # "scan" | "mma" | "scan2" (two-kernel scan) | None (tests / benchmarks)
         self._timing = False
         self._pending: list = []             # tensors of deferred device searches, kept alive until finish_search()
@@ -506,13 +506,14 @@ class VectorBase:
         if subset is not None:
             if type(subset) is list:
                 pack = _capi.pack_int_list()
-                if pack is not None:                 # CPython-API walk of the list: 4 us per 1000 ordinals
-                    buf = self._subset_buf
-                    if buf is None or len(buf) < len(subset):
-                        buf = self._subset_buf = np.empty(max(4096, 2 * len(subset)), np.int64)
-                    got = pack(subset, buf.ctypes.data, len(buf))
+                if pack is not None:                 # CPython-API walk of the list: 3.7 us per 1000 ordinals
+                    buf = self._subset_buf           # (int64 array, its address): reused across calls
+                    if buf is None or len(buf[0]) < len(subset):
+                        arr = np.empty(max(4096, 2 * len(subset)), np.int64)
+                        buf = self._subset_buf = (arr, arr.ctypes.data)
+                    got = pack(subset, buf[1], len(buf[0]))
                     if got >= 0:
-                        sub = buf[:got]
+                        sub, sub_ptr, n_rows, sub_len = buf[0], buf[1], got, got
                 if sub is None:
                     try:
                         sub = np.frombuffer(_array("q", subset), dtype=np.int64)   # 18 us; np.asarray(list): 29 us
@@ -523,8 +524,9 @@ class VectorBase:
                 if sub.size and not np.issubdtype(sub.dtype, np.integer):
                     raise IndexError("arrays used as indices must be of integer (or boolean) type")
                 sub = np.ascontiguousarray(sub.astype(np.int64, copy=False).reshape(-1))
-            n_rows = sub_len = len(sub)
-            sub_ptr = sub.ctypes.data
+            if sub_ptr is None:
+                n_rows = sub_len = len(sub)
+                sub_ptr = sub.ctypes.data
         k_eff = max(1, min(k, n_rows))
         out = self._single_out.get(k_eff)
         if out is None:
@@ -535,7 +537,11 @@ class VectorBase:
                                              counts.ctypes.data)
         items, scores, counts, ip, sp, cp = out
         lib, ix = self._ensure_device()
-        rc = lib.tav_search(ix, q.ctypes.data, 1, k_eff, floor, self._flags(), sub_ptr, sub_len, 0, ip, sp, cp, None)
+        try:                                 # 0.5 us; ndarray.ctypes.data builds a helper object (1.5 us)
+            qp = C.addressof(C.c_char.from_buffer(q))
+        except (TypeError, ValueError):      # read-only query buffer
+            qp = q.ctypes.data
+        rc = lib.tav_search(ix, qp, 1, k_eff, floor, self._flags(), sub_ptr, sub_len, 0, ip, sp, cp, None)
         if rc < 0:
             _capi.check(rc)
         c = int(counts[0])
