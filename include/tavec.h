@@ -179,8 +179,9 @@ int tav_merge_topk(int device, int n_lists, int n_queries, int k, const int64_t*
  * No NCCL call and no host synchronisation on this path.  SPMD: every rank calls it with the same
  * n_queries and k, in the same order.  queries / outputs are device pointers; the merged result is
  * replicated on every rank.  With TAV_DEFER_RETRY in `flags` up to `depth` searches may be
- * outstanding before tav_sharded_finish (which also agrees, across ranks, whether any rank had to
- * redo a query exactly and then repeats the exchange for the last search).
+ * outstanding before tav_sharded_finish, which also agrees, across ranks, which of them had a query
+ * redone exactly by some rank, and repeats the exchange for exactly those (their output buffers must
+ * stay valid until then).
  */
 typedef struct tav_group tav_group;
 int tav_group_handle_bytes(void);

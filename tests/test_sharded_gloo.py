@@ -134,6 +134,87 @@ def test_sharded_lookup_over_gloo(world, n_rows):
     mp.spawn(_worker, args=(world, _free_port(), n_rows), nprocs=world, join=True)
 
 
+class DeferringOracleEngine(OracleShardEngine):
+    """Stand-in for the tensor-core path's deferred exact fallback: a rank in `spoil_ranks` first hands out an
+    EMPTY candidate list for query 0 and puts the real one in place at finish() (as tav_finish_search does)."""
+
+    def __init__(self, rank, spoil_ranks, fail_rank=None):
+        super().__init__()
+        self.rank, self.spoil_ranks, self.fail_rank = rank, spoil_ranks, fail_rank
+        self.fixups = []
+
+    def search_packed(self, queries, k, min_score, item_offset, defer_check=False):
+        from typeagent_py_b200.sharded import packed_layout
+
+        buf = super().search_packed(queries, k, min_score, item_offset)
+        if defer_check and self.rank in self.spoil_ranks:
+            _, off_c, _ = packed_layout(len(queries), k)
+            counts = buf.numpy()[off_c: off_c + 4 * len(queries)].view(np.int32)
+            self.fixups.append((counts, int(counts[0])))
+            counts[0] = 0
+        return buf
+
+    def finish(self):
+        if self.fail_rank == self.rank:
+            self.fixups.clear()
+            raise RuntimeError("exact fallback failed on this rank")
+        n = len(self.fixups)
+        for counts, real in self.fixups:
+            counts[0] = real
+        self.fixups.clear()
+        return n
+
+
+def _deferred_worker(rank: int, world: int, port: int):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from types import SimpleNamespace
+
+        from oracle import vectorbase_oracle as O
+        from typeagent_py_b200.sharded import ShardedVectorBase
+
+        v, q = O.make_corpus(301, 16, seed=3, n_queries=4)
+        settings = SimpleNamespace(embedding_model=O.FakeEmbeddingModel(), min_score=0.85, max_matches=None)
+        sh = ShardedVectorBase(settings, engine=DeferringOracleEngine(rank, spoil_ranks={0}))
+        sh.deserialize(v)
+        # three deferred searches, ONE finish: every one of them is merged again after the correction
+        ks = (5, 9, 3)
+        outs = [sh.search_tensors(q, k, 0.0, defer_check=True) for k in ks]
+        stale = outs[0][0].numpy().copy()
+        assert sh.finish() == 3 and sh.finish() == 0
+        for k, (items, scores, counts) in zip(ks, outs):
+            for i in range(len(q)):
+                want = O.lookup(v, q[i], k, 0.0)
+                assert items[i, : counts[i]].tolist() == [h.item for h in want], (rank, k, i)
+        lo, hi = sh.local_range
+        best0 = O.lookup(v, q[0], 1, 0.0)[0].item
+        if 0 <= best0 < shard_hi(301, world, 0):   # the spoiled rank owned query 0's best row: the first merge missed it
+            assert stale[0, 0] != best0
+        # not deferred: resolved before returning
+        items, _, counts = sh.search_tensors(q, 4, 0.0)
+        assert items[0, : counts[0]].tolist() == [h.item for h in O.lookup(v, q[0], 4, 0.0)]
+        # a rank whose fallback fails must not leave the others in the collective: every rank raises
+        bad = ShardedVectorBase(settings, engine=DeferringOracleEngine(rank, spoil_ranks={1}, fail_rank=1))
+        bad.deserialize(v)
+        bad.search_tensors(q, 5, 0.0, defer_check=True)
+        with pytest.raises(RuntimeError):
+            bad.finish()
+        assert bad.finish() == 0
+    finally:
+        dist.destroy_process_group()
+
+
+def shard_hi(n_rows, world, rank):
+    from typeagent_py_b200.sharded import shard_bounds
+
+    return shard_bounds(n_rows, world)[rank][1]
+
+
+def test_deferred_searches_are_all_repaired_at_finish_over_gloo():
+    mp.spawn(_deferred_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
 def test_shard_bounds_and_packing():
     from typeagent_py_b200.sharded import packed_layout, shard_bounds
 

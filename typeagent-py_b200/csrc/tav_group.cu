@@ -127,12 +127,14 @@ struct tav_group {
     cudaEvent_t ev_local[64] = {};    // [depth] local search of the slot's search done (caller's stream)
     cudaEvent_t ev_merged[64] = {};   // [depth] merged result complete (exchange stream)
     bool x_pending = false;           // something was enqueued on xstream since the last join
-    std::vector<uint32_t> open_seqs;  // sequence numbers of the deferred searches since the last finish
-    int64_t* merged_items = nullptr;  // where the last search's merged result went (for a re-merge at finish)
-    float* merged_scores = nullptr;
-    int32_t* merged_counts = nullptr;
-    int last_nq = 0, last_k = 0;
-    uint32_t last_seq = 0;
+    struct OpenSearch {               // a deferred search since the last finish: what a re-merge needs
+        uint32_t seq;
+        int nq, k;
+        int64_t* items;
+        float* scores;
+        int32_t* counts;
+    };
+    std::vector<OpenSearch> open;     // ascending, consecutive sequence numbers ending at `seq`
     int outstanding = 0;              // deferred sharded searches since the last finish
 };
 
@@ -314,10 +316,16 @@ int tav_sharded_search(tav_index* ix, tav_group* g, const float* queries_device,
     TAVG_CUDA(cudaSetDevice(g->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool defer = (flags & TAV_DEFER_RETRY) != 0;
-    if (defer && g->outstanding >= g->depth) {
-        set_error("tav_sharded_search: %d deferred searches outstanding (the group's depth); call tav_sharded_finish",
-                  g->outstanding);
-        return TAV_ERR_STATE;
+    if (g->outstanding >= g->depth) {
+        // the next sequence number's slot still belongs to the oldest open search
+        if (defer) {
+            set_error("tav_sharded_search: %d deferred searches outstanding (the group's depth); call tav_sharded_finish",
+                      g->outstanding);
+            return TAV_ERR_STATE;
+        }
+        int redone = 0;
+        const int frc = tav_sharded_finish(ix, g, stream, &redone);
+        if (frc != TAV_OK) return frc;
     }
     const uint32_t seq = ++g->seq;
     const int slot = static_cast<int>(seq % static_cast<uint32_t>(g->depth));
@@ -333,7 +341,10 @@ int tav_sharded_search(tav_index* ix, tav_group* g, const float* queries_device,
         int rc = tav_search(ix, queries_device, n_queries, k, min_score, sflags, nullptr, 0, item_offset,
                             reinterpret_cast<int64_t*>(mine), reinterpret_cast<float*>(mine + off_scores),
                             reinterpret_cast<int32_t*>(mine + off_counts), stream);
-        if (rc != TAV_OK) return rc;
+        if (rc != TAV_OK) {
+            --g->seq;  // nothing was published under this number
+            return rc;
+        }
     }
     int n_retry = 0;
     const int32_t* retry_totals = tav_size(ix) == 0 ? nullptr : tav_internal_retry_totals(ix, &n_retry);
@@ -351,13 +362,7 @@ int tav_sharded_search(tav_index* ix, tav_group* g, const float* queries_device,
     int rc = publish_and_merge(g, n_queries, k, seq, retry_totals, n_retry, out_items, out_scores, out_counts, xs);
     if (rc != TAV_OK) return rc;
     if (xs != s) g->x_pending = true;
-    g->open_seqs.push_back(seq);
-    g->merged_items = out_items;
-    g->merged_scores = out_scores;
-    g->merged_counts = out_counts;
-    g->last_nq = n_queries;
-    g->last_k = k;
-    g->last_seq = seq;
+    g->open.push_back({seq, n_queries, k, out_items, out_scores, out_counts});
     g->outstanding += 1;
     if (!defer) {
         int redone = 0;
@@ -385,38 +390,43 @@ int tav_sharded_finish(tav_index* ix, tav_group* g, void* stream, int* redone_to
     // rank has just corrected.  One stream synchronise (tav_finish_search already did it when anything
     // was pending on this rank) makes the mapped words current; no second exchange.
     TAVG_CUDA(cudaStreamSynchronize(s));
-    uint32_t total = static_cast<uint32_t>(redone);
-    if (g->world > 1) {
-        total = 0;
-        for (uint32_t sq : g->open_seqs) total += g->flagged_host[sq % static_cast<uint32_t>(g->depth)];
-    }
-    g->open_seqs.clear();
-    const int outstanding = g->outstanding;
+    // which of the open searches had candidates corrected somewhere in the world (identical on every rank: all
+    // ranks summed the same tails).  Read BEFORE any re-merge reuses a slot.
+    std::vector<tav_group::OpenSearch> open;
+    open.swap(g->open);
     g->outstanding = 0;
+    std::vector<uint32_t> flagged(open.size(), 0);
+    uint32_t total = 0;
+    for (size_t i = 0; i < open.size(); ++i) {
+        // one rank: no tails were exchanged; the local redo count says "something changed", re-merge them all
+        flagged[i] = g->world > 1 ? g->flagged_host[open[i].seq % static_cast<uint32_t>(g->depth)]
+                                  : static_cast<uint32_t>(redone);
+        total += flagged[i];
+    }
+    if (g->world == 1) total = static_cast<uint32_t>(redone);
     if (total > 0) {
-        // Some rank corrected candidates it had already published: exchange and merge again.  Only the
-        // LAST search can be repaired (its slot and output pointers are known); with several deferred
-        // searches outstanding an earlier one may be stale — report it.
-        const uint32_t seq = ++g->seq;
-        const int old_slot = static_cast<int>(g->last_seq % static_cast<uint32_t>(g->depth));
-        const int new_slot = static_cast<int>(seq % static_cast<uint32_t>(g->depth));
-        if (new_slot != old_slot) {
-            size_t os, oc, bytes;
-            packed_offsets(g->last_nq, g->last_k, &os, &oc, &bytes);
-            const char* from = g->region + g->off_slots + (static_cast<size_t>(old_slot) * g->world + g->rank) * g->slot_bytes;
-            char* to = g->region + g->off_slots + (static_cast<size_t>(new_slot) * g->world + g->rank) * g->slot_bytes;
-            TAVG_CUDA(cudaMemcpyAsync(to, from, bytes, cudaMemcpyDeviceToDevice, s));
+        // Some rank corrected (in its own slot, tav_finish_search above) candidates it had already published:
+        // publish and merge those searches again, oldest first.  A repair takes a fresh sequence number, whose
+        // slot is that of an open search no younger than the one being repaired (the open searches are the last
+        // `outstanding` <= depth consecutive ones) — i.e. one that is unflagged or already repaired; its peers'
+        // acknowledgements are what the publish kernel waits for anyway.
+        for (size_t i = 0; i < open.size(); ++i) {
+            if (flagged[i] == 0) continue;
+            const tav_group::OpenSearch& o = open[i];
+            const uint32_t seq = ++g->seq;
+            const int old_slot = static_cast<int>(o.seq % static_cast<uint32_t>(g->depth));
+            const int new_slot = static_cast<int>(seq % static_cast<uint32_t>(g->depth));
+            if (new_slot != old_slot) {
+                size_t os, oc, bytes;
+                packed_offsets(o.nq, o.k, &os, &oc, &bytes);
+                const char* from = g->region + g->off_slots + (static_cast<size_t>(old_slot) * g->world + g->rank) * g->slot_bytes;
+                char* to = g->region + g->off_slots + (static_cast<size_t>(new_slot) * g->world + g->rank) * g->slot_bytes;
+                TAVG_CUDA(cudaMemcpyAsync(to, from, bytes, cudaMemcpyDeviceToDevice, s));
+            }
+            rc = publish_and_merge(g, o.nq, o.k, seq, nullptr, 0, o.items, o.scores, o.counts, s);
+            if (rc != TAV_OK) return rc;
         }
-        rc = publish_and_merge(g, g->last_nq, g->last_k, seq, nullptr, 0, g->merged_items, g->merged_scores,
-                               g->merged_counts, s);
-        if (rc != TAV_OK) return rc;
         TAVG_CUDA(cudaStreamSynchronize(s));
-        if (outstanding > 1) {
-            if (redone_total) *redone_total = static_cast<int>(total);
-            set_error("tav_sharded_finish: %u queries needed the exact fallback while %d sharded searches were "
-                      "outstanding; only the last one was re-merged", total, outstanding);
-            return TAV_ERR_STATE;
-        }
     }
     if (redone_total) *redone_total = static_cast<int>(total);
     return TAV_OK;

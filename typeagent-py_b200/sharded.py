@@ -214,6 +214,7 @@ class ShardedVectorBase:
         self._engine = engine
         self._starts = [0] * (self.world + 1)  # global row where each rank's block starts
         self._embedding_size = 0
+        self._pending: list = []  # deferred searches since the last finish(): ["group"] or (local, b, k, out) tuples
 
     # ---- corpus ------------------------------------------------------------------------
     def __len__(self) -> int:
@@ -299,13 +300,18 @@ class ShardedVectorBase:
         if self.exchange == "peer" and self.world > 1 and hasattr(self._engine, "group_search"):
             out = self._engine.group_search(self._dist, self._group, self.rank, self.world, queries, k,
                                             float(np.float32(min_score)), lo, defer_check)
-            self._pending = ("group",) if defer_check else None
+            self._pending = ["group"] if defer_check else []
             return out
         deferrable = hasattr(self._engine, "finish")
         local = (self._engine.search_packed(queries, k, float(np.float32(min_score)), lo, defer_check=True)
                  if deferrable else self._engine.search_packed(queries, k, float(np.float32(min_score)), lo))
         out = self._gather_and_merge(local, b, k)
-        self._pending = (local, b, k, out) if deferrable else None
+        pending = getattr(self, "_pending", None) or []
+        if pending == ["group"]:
+            pending = []
+        if deferrable:
+            pending.append((local, b, k, out))
+        self._pending = pending
         if not defer_check:
             self.finish()
         return out
@@ -316,13 +322,11 @@ class ShardedVectorBase:
         import torch
 
         pending = getattr(self, "_pending", None)
-        if pending is None:
+        if not pending:
             return 0
-        if pending == ("group",):      # libtavec agrees across ranks inside tav_sharded_finish
-            self._pending = None
+        self._pending = []
+        if pending == ["group"]:       # libtavec agrees across ranks inside tav_sharded_finish
             return self._engine.group_finish()
-        local, b, k, out = pending
-        self._pending = None
         # a local failure must not leave the other ranks waiting in the collective: reduce an error
         # flag together with the count and raise on every rank
         error = None
@@ -332,14 +336,15 @@ class ShardedVectorBase:
             error, redone = e, 0
         total, failed = redone, int(error is not None)
         if self.world > 1:
-            t = torch.tensor([redone, failed], dtype=torch.int32, device=local.device)
+            t = torch.tensor([redone, failed], dtype=torch.int32, device=pending[-1][0].device)
             self._dist.all_reduce(t, group=self._group)
             total, failed = int(t[0].item()), int(t[1].item())
         if failed:
             raise error if error is not None else RuntimeError("finish(): another rank failed its exact fallback")
-        if total > 0:  # some shard corrected its candidates: exchange and merge again, in place
-            items, scores, counts = self._gather_and_merge(local, b, k)
-            out[0].copy_(items), out[1].copy_(scores), out[2].copy_(counts)
+        if total > 0:  # some shard corrected its candidates (in place): exchange and merge every open search again
+            for local, b, k, out in pending:
+                items, scores, counts = self._gather_and_merge(local, b, k)
+                out[0].copy_(items), out[1].copy_(scores), out[2].copy_(counts)
         return total
 
     def search_arrays(self, queries: np.ndarray, k: int, min_score: float = 0.0):
