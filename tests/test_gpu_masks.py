@@ -73,6 +73,23 @@ def test_predicate_max_hits_zero_and_empty_results():
     assert base.fuzzy_lookup_embedding(q[0], 5, 0.999, predicate=lambda i: True) == []
 
 
+def test_predicate_cache_survives_recycled_ids_and_can_be_cleared():
+    v, q = O.make_corpus(3000, 32, seed=12, n_queries=1)
+    base = make_base(v)
+    # many short-lived predicates (the cache holds 8; CPython hands a collected lambda's id to the next one)
+    for m in range(2, 24):
+        got = base.fuzzy_lookup_embedding(q[0], 7, 0.0, predicate=lambda i, m=m: i % m == 1)
+        want = O.lookup(v, q[0], 7, 0.0, predicate=lambda i, m=m: i % m == 1)
+        assert [h.item for h in got] == [h.item for h in want], m
+    # a predicate whose meaning changes between lookups: cached per function object until told otherwise
+    allowed = {5, 17, 300}
+    pred = lambda i: i in allowed  # noqa: E731
+    assert sorted(h.item for h in base.fuzzy_lookup_embedding(q[0], 10, 0.0, predicate=pred)) == [5, 17, 300]
+    allowed.add(1234)
+    base.clear_predicate_cache()
+    assert sorted(h.item for h in base.fuzzy_lookup_embedding(q[0], 10, 0.0, predicate=pred)) == [5, 17, 300, 1234]
+
+
 def test_large_index_predicate_tries_one_page_then_the_mask():
     v, q = O.make_corpus(70000, 32, seed=5, n_queries=2)
     base = make_base(v)

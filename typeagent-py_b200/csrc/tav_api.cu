@@ -145,6 +145,7 @@ struct tav_index {
     PinBuf pin_out;     // pinned staging: packed results on the way out (+ the completion word)
     PinBuf pin_append[2];             // bulk load: pinned double buffer
     cudaEvent_t ev_append[2] = {nullptr, nullptr};
+    bool append_busy[2] = {false, false};  // an H2D copy recorded under ev_append[b] may still read pin_append[b]
     cudaEvent_t ev_pin_in = nullptr;  // completion of the last H2D that read pin_in
     bool pin_in_busy = false;
     uint32_t done_seq = 0;            // completion word sequence of the single-launch form
@@ -397,11 +398,13 @@ int tav_append(tav_index* ix, const void* rows, int64_t n, int dim, int src_dtyp
         const size_t stage_bytes = static_cast<size_t>(std::min(n, chunk_rows)) * src_row;
         if (!plain) TAV_CUDA(ix->staging.ensure(2 * stage_bytes));
         int b = 0;
-        bool used[2] = {false, false};
         for (int64_t done = 0; done < n; done += chunk_rows, b ^= 1) {
             const int64_t m = std::min(chunk_rows, n - done);
             const size_t bytes = static_cast<size_t>(m) * src_row;
-            if (used[b]) TAV_CUDA(cudaEventSynchronize(ix->ev_append[b]));
+            if (ix->append_busy[b]) {  // also across calls: the previous append may still be queued on its stream
+                TAV_CUDA(cudaEventSynchronize(ix->ev_append[b]));
+                ix->append_busy[b] = false;
+            }
             TAV_CUDA(ix->pin_append[b].ensure(stage_bytes));
             memcpy(ix->pin_append[b].p, static_cast<const char*>(rows) + done * src_row, bytes);
             if (plain) {
@@ -412,7 +415,7 @@ int tav_append(tav_index* ix, const void* rows, int64_t n, int dim, int src_dtyp
                 TAV_CUDA(launch_convert(stage, src_dtype, dst + done * dst_row, ix->dtype, m, ix->dim, norm, s));
             }
             TAV_CUDA(cudaEventRecord(ix->ev_append[b], s));
-            used[b] = true;
+            ix->append_busy[b] = true;
         }
         // the caller's buffer was fully consumed by the memcpys above; the pinned buffers are
         // re-acquired through their events, so no synchronisation is needed here
@@ -858,7 +861,7 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
         a.floor_score = min_score;
         a.k = k;
         a.grid = scan1_grid(ix->device, ix->dim, k, n_scan);
-        a.cand_stride = a.grid * std::max(k, 32);   // a CTA hands over up to one round of 32 rows unsorted
+        a.cand_stride = a.grid * std::max(k, 32);   // a CTA hands over its k best (room for a round of 32 rows)
         TAV_CUDA(ix->cand_keys.ensure(static_cast<size_t>(a.cand_stride) * sizeof(uint64_t)));
         a.cand_keys = static_cast<uint64_t*>(ix->cand_keys.p);
         a.cand_count = d_count;

@@ -131,6 +131,7 @@ class VectorBase:
         self._timing = False
         self._pending: list = []             # tensors of deferred device searches, kept alive until finish_search()
         self._mask_key = None                # identity of the row mask currently on the device
+        self._mask_ref = None                # ... and the object(s) that identity belongs to (so id() cannot be recycled)
         self._predicate_masks: dict = {}     # (id(predicate), generation, n) -> packed bitmask
         self.clear()
 
@@ -340,20 +341,24 @@ class VectorBase:
             bits = np.concatenate([bits, np.zeros(pad, np.uint8)])
         return np.ascontiguousarray(bits).view(np.uint32)
 
-    def _use_row_mask(self, lib, ix, allowed, key=None) -> None:
+    def _use_row_mask(self, lib, ix, allowed, key=None, owner=None) -> None:
         """Upload ``allowed`` (bool [N], or packed uint32 words) unless it is the mask already
-        on the device.  Masks are treated as immutable: identity + row generation is the key."""
+        on the device.  Masks are treated as immutable: identity + row generation is the key
+        (``owner``: the object whose id() a caller-made key is built on — kept alive here, as is
+        ``allowed``, because the id of a collected object can be handed to a new one)."""
         n = len(self)
         if key is None:
             key = (id(allowed), self._generation, n)
         if self._mask_key == key:
             return
+        self._mask_key = None
         words = allowed if getattr(allowed, "dtype", None) == np.uint32 else self.pack_row_mask(allowed)
         if len(words) != (n + 31) // 32:
             raise ValueError(f"row mask has {len(words) * 32} bits for {n} rows")
         words = np.ascontiguousarray(words)
         _capi.check(lib.tav_set_row_mask(ix, words.ctypes.data_as(C.c_void_p), n, 0, None))
         self._mask_key = key
+        self._mask_ref = (allowed, owner)
 
     def _check_queries(self, queries) -> np.ndarray:
         q = np.ascontiguousarray(queries, dtype=np.float32)
@@ -375,6 +380,7 @@ class VectorBase:
         allowed: np.ndarray | None = None,
         ties_low_first: bool = False,
         _mask_key=None,
+        _mask_owner=None,
     ) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
         """Batched lookup returning arrays: items int64 [B, k], scores float32 [B, k],
         counts int32 [B] (entries beyond counts[b] are padding: item -1, score 0).  `k` is
@@ -415,7 +421,7 @@ class VectorBase:
         if allowed is not None:
             if sub is not None:
                 raise ValueError("allowed= and subset= cannot be combined")
-            self._use_row_mask(lib, ix, allowed, _mask_key)
+            self._use_row_mask(lib, ix, allowed, _mask_key, _mask_owner)
             flags |= _capi.TAV_USE_ROW_MASK
         if ties_low_first:
             flags |= _capi.TAV_TIES_LOW_FIRST
@@ -561,6 +567,13 @@ class VectorBase:
             hit = self._predicate_masks[key] = (self.pack_row_mask(accepted), predicate)  # keeps id() alive
         return hit[0], key
 
+    def clear_predicate_cache(self) -> None:
+        """Forget the cached predicate bitmasks (and the mask on the device): for predicates whose
+        answer changed since they were last used."""
+        self._predicate_masks.clear()
+        self._mask_key = None
+        self._mask_ref = None
+
     def _lookup_with_predicate(self, embedding, k, min_score, predicate) -> list[ScoredInt]:
         """Reference semantics (vectorbase.py:191-201): every row at or above min_score that
         satisfies the predicate, stable-sorted by descending score, first k.
@@ -588,7 +601,7 @@ class VectorBase:
                 return accepted[:k]
         mask, key = self._predicate_mask(predicate)
         items, scores, counts = self.search_arrays(embedding, k, min_score, allowed=mask,
-                                                   ties_low_first=True, _mask_key=key)
+                                                   ties_low_first=True, _mask_key=key, _mask_owner=predicate)
         c = int(counts[0])
         return [ScoredInt(i, s_) for i, s_ in zip(items[0, :c].tolist(), scores[0, :c].tolist())]
 
