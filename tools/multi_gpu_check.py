@@ -77,18 +77,20 @@ def main():
     for exchange in ("peer", "nccl"):
         sh = ShardedVectorBase(settings, device=local, storage_dtype="bfloat16", exchange=exchange)
         sh.deserialize(same)
-        items, scores, counts = sh.search_arrays(np.repeat(row, 3, axis=0), 6, 0.0)
+        nq = 16   # enough queries for the tensor-core path (fewer go to the exact row scan directly)
+        items, scores, counts = sh.search_arrays(np.repeat(row, nq, axis=0), 6, 0.0)
         n = len(same)
-        assert items.tolist() == [list(range(n - 1, n - 7, -1))] * 3, items
+        assert sh._engine.base.last_timing()["path"] == "mma"
+        assert items.tolist() == [list(range(n - 1, n - 7, -1))] * nq, items
         # three deferred searches of the same pathological corpus, ONE finish: every one of them is repaired
-        qd = torch.from_numpy(np.repeat(row, 3, axis=0)).cuda()
+        qd = torch.from_numpy(np.repeat(row, nq, axis=0)).cuda()
         ks = (6, 4, 9)
         outs = [sh.search_tensors(qd, kk, 0.0, defer_check=True) for kk in ks]
         assert sh.finish() > 0
         torch.cuda.synchronize()
         for kk, (it, sc, ct) in zip(ks, outs):
-            assert ct.cpu().tolist() == [kk] * 3, ct
-            assert it.cpu().tolist() == [list(range(n - 1, n - 1 - kk, -1))] * 3, (kk, it)
+            assert ct.cpu().tolist() == [kk] * nq, ct
+            assert it.cpu().tolist() == [list(range(n - 1, n - 1 - kk, -1))] * nq, (kk, it)
         if rank == 0:
             print(f"multi-gpu ok: world={world} exact fallback through finish(), one and three outstanding, "
                   f"exchange={exchange}", flush=True)

@@ -14,6 +14,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -95,6 +96,10 @@ constexpr size_t kAppendStageBytes = size_t(32) << 20; // pinned double buffer o
 // the single-launch row scan runs one wave of CTAs (its last CTA merges): a latency form for corpora that
 // fit L2; bigger scans want 4 CTAs per SM in flight and take the two-kernel form
 constexpr size_t kFusedScanMaxBytes = size_t(32) << 20;
+// single-launch form, k up to this: the host watches the mapped result slots instead of a completion word
+constexpr int kWatchSlotsMaxK = 64;
+constexpr int64_t kNoItemYet = INT64_MIN;        // no hit has this ordinal ...
+constexpr uint32_t kNoScoreYet = 0xFFFFFFFFu;    // ... or this score (a NaN pattern; scores are clipped to [0, 1])
 
 // CUDA events around one search (created lazily, when timing is first enabled)
 struct TimedSearch {
@@ -874,11 +879,28 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
         a.out_items = d_items;
         a.out_scores = d_scores;
         a.out_counts = d_counts;
+        // Completion.  Small k: NO completion word and no system-scope fence in the kernel (that fence waits
+        // ~1.8 us for the result stores to cross PCIe before the word may follow them): the host pre-fills the
+        // mapped result slots with values no hit can have and watches the slots themselves — the count and
+        // all k items and scores; every slot is one aligned store, so it arrives whole.  Larger k: one
+        // completion word behind a fence.
+        const bool watch_slots = k <= kWatchSlotsMaxK;
         volatile uint32_t* done = reinterpret_cast<volatile uint32_t*>(static_cast<char*>(ix->pin_out.p) + off_done);
-        a.done_flag = const_cast<uint32_t*>(done);
-        a.done_seq = ++ix->done_seq;
-        if (a.done_seq == 0) a.done_seq = ++ix->done_seq;
-        *done = 0;
+        volatile int64_t* w_items = reinterpret_cast<volatile int64_t*>(d_items);
+        volatile uint32_t* w_scores = reinterpret_cast<volatile uint32_t*>(d_scores);
+        volatile int32_t* w_count = reinterpret_cast<volatile int32_t*>(d_counts);
+        if (watch_slots) {
+            for (int j = 0; j < k; ++j) {
+                w_items[j] = kNoItemYet;
+                w_scores[j] = kNoScoreYet;
+            }
+            *w_count = -1;
+        } else {
+            a.done_flag = const_cast<uint32_t*>(done);
+            a.done_seq = ++ix->done_seq;
+            if (a.done_seq == 0) a.done_seq = ++ix->done_seq;
+            *done = 0;
+        }
         static const bool trace_on = getenv("TAV_TRACE") != nullptr;
         unsigned long long* trace_host = nullptr;
         unsigned long long t_host0 = 0;
@@ -909,13 +931,25 @@ int tav_search(tav_index* ix, const float* queries, int n_queries, int k, float 
         // back to the synchronise when the word does not show up quickly (error, or a busy GPU)
         bool seen = false;
         for (int spin = 0; spin < 4000000; ++spin) {
-            if (*done == a.done_seq) {
+            if (watch_slots) {
+                // ALL k slots (the kernel also writes the padding beyond `count`): once they are in, no store
+                // of this launch is still on its way to the buffer the next call pre-fills
+                if (*w_count >= 0) {
+                    int j = 0;
+                    while (j < k && w_items[j] != kNoItemYet && w_scores[j] != kNoScoreYet) ++j;
+                    if (j >= k) {
+                        seen = true;
+                        break;
+                    }
+                }
+            } else if (*done == a.done_seq) {
                 seen = true;
                 break;
             }
             if ((spin & 0x3FFF) == 0x3FFF && cudaStreamQuery(s) != cudaErrorNotReady) break;
         }
         if (!seen) TAV_CUDA(cudaStreamSynchronize(s));
+        std::atomic_thread_fence(std::memory_order_acquire);  // the copies below read what the spin saw
         if (trace_host) {
             timespec tsn;
             clock_gettime(CLOCK_MONOTONIC, &tsn);
