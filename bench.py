@@ -645,7 +645,8 @@ def measure(bn: Bench, name, w, steps, warmup, *, force=None, sustain_s=0.0, par
         "metric": metric_string(w),
         "value": qps, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": {"float32": "f32", "bfloat16": "bf16", "float16": "f16"}[storage] + " in, f32 accumulate",
+        "dtype": {"float32": "f32", "bfloat16": "bf16", "float16": "f16"}[storage],
+        "dtype_detail": "operands in the storage dtype, float32 accumulate, float32 scores (the reference: float32 throughout)",
         "data": "synthetic (unit-norm gaussian rows, generated on device; seeds in bench.py)",
         "config": workload_config(w, world),
         "path": path,
