@@ -26,6 +26,7 @@ every path except the predicate path, which keeps the reference's stable "lower 
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from array import array as _array
 from collections.abc import Callable, Sequence
 from dataclasses import dataclass
@@ -127,6 +128,7 @@ class VectorBase:
         self._adopted_tensor = None
         self._single_out: dict[int, tuple] = {}  # k -> reusable result arrays of fuzzy_lookup_embedding
         self._subset_buf: tuple | None = None  # (reusable int64 buffer for list subsets, its address)
+        self._single_lock = threading.Lock()   # guards the two reusable buffers above
         self.force_path: str | None = None  # "scan" | "mma" | "scan2" (two-kernel scan) | None (tests / benchmarks)
         self._timing = False
         self._pending: list = []             # tensors of deferred device searches, kept alive until finish_search()
@@ -491,6 +493,11 @@ class VectorBase:
         return self._lookup_one(embedding, k, min_score, None)
 
     def _lookup_one(self, embedding, k: int, min_score: float, subset) -> list[ScoredInt]:
+        # the reused result / subset buffers belong to one lookup at a time (ctypes releases the GIL in tav_search)
+        with self._single_lock:
+            return self._lookup_one_locked(embedding, k, min_score, subset)
+
+    def _lookup_one_locked(self, embedding, k: int, min_score: float, subset) -> list[ScoredInt]:
         """Single-lookup latency path (tools/benchmark_vectorbase.py:97-158 is this call): one host
         query straight into ``tav_search`` — which serves it with ONE kernel launch, the query riding
         in the kernel parameters — with reused result buffers and cached ctypes pointers; none of
