@@ -1027,8 +1027,13 @@ Plan make_plan(int device, int64_t n_rows, int dim, int nq, int k, bool split, b
     // row scan.  Large corpora aim at 2048 rows, small ones at 128; never fewer than 16k.
     // For k <= 8 nothing can starve, so small corpora aim much lower (32 rows: a quarter of the corpus is
     // sampled, with the branch-free epilogue, and MAIN's epilogue then rarely has anything to append).
+    static const int64_t small_k_floor = [] {
+        const char* e = getenv("TAV_SMALLK_TARGET");  // tuning knob (profiles/r02_c5_target_sweep.log)
+        const int64_t v = e ? atoll(e) : 0;
+        return v >= 8 ? v : int64_t(32);
+    }();
     const int64_t target = k <= kSampleTop
-                               ? std::min<int64_t>(2048, std::max<int64_t>(32, n_rows / 4096))
+                               ? std::min<int64_t>(2048, std::max<int64_t>(small_k_floor, n_rows / 4096))
                                : std::max<int64_t>(16ll * k, std::min<int64_t>(2048, std::max<int64_t>(128, n_rows / 4096)));
     int64_t admitted = n_rows;  // rows a query is expected to admit
     if (n_rows <= 16384 || 8 * target >= n_rows || p.n_full_tiles < 8) {
