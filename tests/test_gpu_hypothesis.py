@@ -3,7 +3,6 @@ dtypes against the CPU oracle — the ragged / degenerate corners seeded tests d
 
 from __future__ import annotations
 
-import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings
 from hypothesis import strategies as st

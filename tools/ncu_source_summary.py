@@ -3,7 +3,7 @@
 
 usage: ncu -i prof.ncu-rep --page source --csv > src.csv; python tools/ncu_source_summary.py src.csv [kernel-substr] [top]
 """
-import csv, io, sys
+import csv, sys
 
 def sections(path):
     cur = None
