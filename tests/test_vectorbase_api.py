@@ -244,3 +244,54 @@ def test_host_helper_packs_int_lists_and_declines_everything_else():
     for declined in ([1, True], (1, 2), [1, 2**70], [1.0], [np.int64(3)], "ab", None):
         assert pack(declined, buf.ctypes.data, 8) == -1
     assert pack(list(range(9)), buf.ctypes.data, 8) == -2
+
+
+def test_single_lookup_host_path_against_a_fake_library():
+    """Host logic of the latency path (`_lookup_one`) without a GPU: a stand-in for libtavec.tav_search reads
+    the query / subset through the raw addresses the class passes and writes hits through the output
+    addresses — pointer extraction, the CPython-API subset packing and its fallbacks, buffer reuse, k clamp."""
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal((50, 8)).astype(np.float32)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    base = make_gpu()
+    base.add_embeddings(None, v)
+    seen = []
+
+    class FakeLib:
+        @staticmethod
+        def tav_search(ix, qp, nq, k, floor, flags, sub_ptr, sub_len, item_offset, ip, sp, cp, stream):
+            q = np.ctypeslib.as_array(C.cast(qp, C.POINTER(C.c_float)), (8,)).copy()
+            sub = None if not sub_ptr else np.ctypeslib.as_array(C.cast(sub_ptr, C.POINTER(C.c_int64)), (sub_len,)).copy()
+            seen.append((q, sub, k))
+            rows = v if sub is None else v[sub]
+            want = O.lookup(rows, q, k, float(floor))
+            items = np.ctypeslib.as_array(C.cast(ip, C.POINTER(C.c_int64)), (k,))
+            scores = np.ctypeslib.as_array(C.cast(sp, C.POINTER(C.c_float)), (k,))
+            for j, h in enumerate(want):
+                items[j], scores[j] = (h.item if sub is None else int(sub[h.item])), h.score
+            C.cast(cp, C.POINTER(C.c_int32))[0] = len(want)
+            return 0
+
+    base._ensure_device = lambda: (FakeLib, None)
+    q = v[3].copy()
+    got = base.fuzzy_lookup_embedding(q, 4, 0.0)
+    assert [h.item for h in got] == [h.item for h in O.lookup(v, q, 4, 0.0)] and got[0].item == 3
+    ro = q.copy()
+    ro.flags.writeable = False                      # read-only query: the slower pointer path
+    assert [h.item for h in base.fuzzy_lookup_embedding(ro, 4, 0.0)] == [h.item for h in got]
+    assert base.fuzzy_lookup_embedding(list(map(float, q)), 2, 0.0)[0].item == 3   # any float sequence
+    # subsets: exact list of ints (packed by libtavhost when built), numpy ints and bools (generic path), arrays
+    for subset in ([7, 3, 11, 3], [np.int64(7), 3, 11], [7, True, 3], np.array([7, 3, 11], np.int32)):
+        hits = base.fuzzy_lookup_embedding_in_subset(q, subset, 10, 0.0)
+        expect = [int(x) for x in np.asarray(subset, dtype=np.int64)]
+        assert seen[-1][1].tolist() == expect and seen[-1][2] == len(expect)      # k clamped to the subset
+        assert hits[0].item == 3 and {h.item for h in hits} <= set(expect)
+    with pytest.raises(IndexError):
+        base.fuzzy_lookup_embedding_in_subset(q, [1.5, 2.0], 3, 0.0)
+    with pytest.raises(ValueError):
+        base.fuzzy_lookup_embedding(np.zeros(9, np.float32), 3, 0.0)
+    assert base.fuzzy_lookup_embedding(q, 3, float("nan")) == []
+    assert base.fuzzy_lookup_embedding_in_subset(q, [], 3, 0.0) == []
+    # a longer list than the reusable buffer grows it
+    big = list(range(50)) * 100
+    assert len(base.fuzzy_lookup_embedding_in_subset(q, big, 5, 0.0)) == 5 and seen[-1][1].tolist() == big
