@@ -354,7 +354,12 @@ class VectorBase:
         if self._mask_key == key:
             return
         self._mask_key = None
-        words = allowed if getattr(allowed, "dtype", None) == np.uint32 else self.pack_row_mask(allowed)
+        if getattr(allowed, "dtype", None) == np.uint32:
+            words = allowed
+        else:
+            if len(allowed) != n:
+                raise ValueError(f"row mask has {len(allowed)} entries for {n} rows")
+            words = self.pack_row_mask(allowed)
         if len(words) != (n + 31) // 32:
             raise ValueError(f"row mask has {len(words) * 32} bits for {n} rows")
         words = np.ascontiguousarray(words)
