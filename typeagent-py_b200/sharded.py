@@ -366,10 +366,8 @@ class ShardedVectorBase:
             return [[] for _ in range(len(embeddings))]
         k = VectorBase._resolve_k(max_hits, len(self))
         items, scores, counts = self.search_arrays(embeddings, k, min_score)
-        return [
-            [ScoredInt(i, s) for i, s in zip(items[b, : counts[b]].tolist(), scores[b, : counts[b]].tolist())]
-            for b in range(len(items))
-        ]
+        il, sl, cl = items.tolist(), scores.tolist(), counts.tolist()
+        return [[ScoredInt(i, s) for i, s in zip(il[b][:c], sl[b][:c])] for b, c in enumerate(cl)]
 
     def fuzzy_lookup_embedding(self, embedding, max_hits=None, min_score=None):
         return self.fuzzy_lookup_embeddings(np.asarray(embedding, np.float32).reshape(1, -1),
